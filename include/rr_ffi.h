@@ -1,0 +1,210 @@
+/*
+ * rr_ffi.h — C ABI of the B200 per-pixel tracing path (libray_rust_b200.so).
+ *
+ * This is the drop-in boundary for ray-rust's `render()`:
+ *
+ *   pub fn render(ren: &RenderEnv, pointproc: &mut impl FnMut(i32, i32, &RenderColor),
+ *                 thread_count: i32) -> anyhow::Result<()>         (reference src/render.rs:801-805)
+ *
+ * The reference has no FFI of its own; `render()` *is* the seam (callers: src/main.rs:338,
+ * src/render.rs:979, src/webserver.rs:48).  A Rust `-sys` crate binds exactly the entry points
+ * below (see INTEGRATION.md for the stub); the C++ host layer in ray-rust_b200/host/ and the
+ * Python ctypes binding in ray-rust_b200/__init__.py are the two bindings built and tested here.
+ *
+ * Conventions
+ *   - POD only. No callbacks cross the ABI. No exceptions / panics cross the ABI.
+ *   - Every function returns int: RR_OK (0) or a negative rr_status. The message for the last
+ *     failure on the calling thread is returned by rr_last_error().
+ *   - All floats are IEEE-754 binary32, all colour channels are linear f32 as in RenderColor
+ *     (src/render.rs:23-28); RGB8 output is `(c*255).min(255) as u8` (src/main.rs:148-152).
+ *   - A scene handle may be used from several host threads concurrently (the web server calls
+ *     render() from several tokio workers, src/webserver.rs:268-280); calls on one handle are
+ *     serialised by a per-handle mutex.
+ *   - The device path is the only path: if no CUDA device is usable every entry point fails with
+ *     RR_ERR_CUDA. There is no CPU fallback inside this library.
+ */
+#ifndef RR_FFI_H
+#define RR_FFI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RR_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------------------------ */
+/* status codes                                                                                */
+/* ------------------------------------------------------------------------------------------ */
+typedef enum rr_status {
+    RR_OK = 0,
+    RR_ERR_BAD_ARG = -1,     /* null pointer, negative size, out-of-range index ...              */
+    RR_ERR_CUDA = -2,        /* any CUDA runtime failure (message carries cudaGetErrorString)    */
+    RR_ERR_OOM = -3,         /* host or device allocation failed                                 */
+    RR_ERR_UNSUPPORTED = -4  /* a scene the device path cannot represent (see rr_scene_create)   */
+} rr_status;
+
+/* ------------------------------------------------------------------------------------------ */
+/* scene description (host side, read once by rr_scene_create)                                 */
+/* ------------------------------------------------------------------------------------------ */
+
+/* RenderObject enum, src/render.rs:585-589 */
+typedef enum rr_object_kind { RR_SPHERE = 0, RR_FLOOR = 1 } rr_object_kind;
+/* UVMap, src/render.rs:51-57 */
+typedef enum rr_uvmap { RR_UV_XY = 0, RR_UV_YZ = 1, RR_UV_ZX = 2, RR_UV_LL = 3 } rr_uvmap;
+/* RenderPattern, src/render.rs:44-49 */
+typedef enum rr_pattern { RR_SOLID = 0, RR_CHECKERBOARD = 1, RR_REPEATED_GRADATION = 2 } rr_pattern;
+/* TextureFilter, src/render.rs:59-63 */
+typedef enum rr_texture_filter { RR_NEAREST = 0, RR_BILINEAR = 1 } rr_texture_filter;
+/* RenderEnv.bgproc is a host fn pointer (src/render.rs:661) and cannot cross to the device.
+ * The only implementation in the reference is `bgcolor` (src/main.rs:231-260). */
+typedef enum rr_bg_kind { RR_BG_BGCOLOR = 0, RR_BG_BLACK = 1 } rr_bg_kind;
+
+/* RenderMaterial, src/render.rs:82-97 (name/texture_name stay on the host). */
+typedef struct rr_material {
+    float diffuse[3];           /* r,g,b */
+    float specular[3];
+    int32_t pn;                 /* Phong exponent for powi */
+    float t;                    /* transparency == refraction blend weight (src/render.rs:1095) */
+    float n;                    /* "refraction constant" (src/render.rs:1098) */
+    float glow_dist;
+    float frac[3];              /* carried for round-trips only; never read by the path */
+    int32_t pattern;            /* rr_pattern */
+    float pattern_scale;
+    float pattern_angle_scale;
+    int32_t texture;            /* index into rr_scene_desc.textures, or -1 for None */
+    int32_t texture_filter;     /* rr_texture_filter */
+} rr_material;
+
+/* RenderSphere (src/render.rs:378-384) / RenderFloor (src/render.rs:487-493). */
+typedef struct rr_object {
+    int32_t kind;               /* rr_object_kind */
+    int32_t material;           /* index into rr_scene_desc.materials */
+    int32_t uvmap;              /* rr_uvmap */
+    float r;                    /* sphere radius; ignored for floors */
+    float org[3];               /* centre */
+    float face_normal[3];       /* floors only; used as given, never normalised */
+} rr_object;
+
+/* DynamicImage::ImageRgb8 — the only texture format the path honours (src/render.rs:251). */
+typedef struct rr_texture {
+    uint32_t width, height;
+    const uint8_t *rgb8;        /* width*height*3, row-major, no padding */
+} rr_texture;
+
+typedef struct rr_scene_desc {
+    uint32_t n_objects;
+    const rr_object *objects;   /* order is significant: index 0 ends the bounce loop (render.rs:1187) */
+    uint32_t n_materials;
+    const rr_material *materials;
+    uint32_t n_textures;
+    const rr_texture *textures;
+} rr_scene_desc;
+
+/* ------------------------------------------------------------------------------------------ */
+/* per-frame parameters: the RenderEnv fields the path reads per ray (src/render.rs:646-666)   */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct rr_frame_params {
+    int32_t xres, yres;
+    float xfov, yfov;
+    float cam_position[3];      /* Camera.position */
+    float cam_rotation[4];      /* Camera.rotation as x,y,z,w (Quat, src/quat.rs:6-11) */
+    float light[3];             /* already normalised by RenderEnv::light (render.rs:720-723) */
+    int32_t use_raymarching;    /* 0: raytrace (render.rs:1142), 1: raymarch (render.rs:1299) */
+    int32_t glow_enabled;       /* glow_effect.is_some() */
+    float glow_effect;
+    int32_t max_reflections;    /* honoured by raytrace only (render.rs:1195 vs :1368) */
+    int32_t max_refractions;
+    int32_t bg_kind;            /* rr_bg_kind */
+    /* Row-band sharding (multi-GPU). Rows are grouped in bands of `band_rows`; band b belongs to
+     * shard (b % band_count); this call renders only the bands of shard `band_index`, packed
+     * contiguously in band order. band_count<=1 renders the whole frame. */
+    int32_t band_rows;
+    int32_t band_index;
+    int32_t band_count;
+} rr_frame_params;
+
+/* per-class ray counters written by rr_render_count (definition of "ray": SURVEY.md 8d) */
+typedef struct rr_ray_counts {
+    uint64_t pixels;
+    uint64_t primary;           /* first raycast()/raymarch_single() of a top-level trace */
+    uint64_t reflect;           /* further iterations of a bounce loop */
+    uint64_t refract;           /* first iteration of a refraction child */
+    uint64_t shadow;            /* shadow raycast()/raymarch_single() inside shading() */
+    uint64_t object_tests;      /* trace: per-object raycast calls; march: per-object distance calls */
+    uint64_t march_steps;       /* march mode: iterations of raymarch_single's loop */
+    uint64_t bg_evals;          /* bgproc invocations (reference-equivalent count) */
+} rr_ray_counts;
+
+typedef struct rr_scene rr_scene; /* opaque: device-resident flattened scene + per-handle stream */
+
+/* ------------------------------------------------------------------------------------------ */
+/* entry points                                                                                */
+/* ------------------------------------------------------------------------------------------ */
+
+/* ABI version of the loaded library (== RR_ABI_VERSION). */
+int rr_abi_version(void);
+
+/* Thread-local message of the last failure on this thread ("" if none). Never NULL. */
+const char *rr_last_error(void);
+
+/* Number of CUDA devices visible to the process. */
+int rr_device_count(int *count);
+
+/* Flatten `desc` (RenderEnv.objects + materials + textures, src/render.rs:658-659) to SoA arrays
+ * on `device` and return a handle. Replaces the immutable borrow `ren: &RenderEnv` that
+ * render() shares with its worker threads (src/render.rs:845-868).
+ * RR_ERR_BAD_ARG on dangling material/texture indices or unknown enum values. */
+int rr_scene_create(const rr_scene_desc *desc, int device, rr_scene **out);
+int rr_scene_destroy(rr_scene *scene);
+
+/* Size in bytes of the packed RGB8 output for `params` (all rows, or this shard's rows). */
+int rr_frame_rows(const rr_frame_params *params, int32_t *rows_out);
+
+/* render(): RGB8, result in HOST memory. Replaces `render(&ren, &mut putpoint, threads)` +
+ * the putpoint quantiser at all three call sites (src/main.rs:148-152,338; src/render.rs:973-979;
+ * src/webserver.rs:42-48). out[(x + y*xres)*3 + c]; `row_stride` in bytes (0 => xres*3).
+ * Blocking. The timed region of bench.py's `e2e` is exactly one call of this function. */
+int rr_render_rgb8(rr_scene *scene, const rr_frame_params *params, uint8_t *out, size_t row_stride);
+
+/* render(): unquantised RenderColor stream (r,g,b f32 per pixel, row-major) in HOST memory, for
+ * callers whose pointproc is not the stock quantiser (generic `pointproc(x, y, &RenderColor)`). */
+int rr_render_f32(rr_scene *scene, const rr_frame_params *params, float *out_rgb);
+
+/* Same kernels, result left in DEVICE memory on `device` of the handle. `cuda_stream` is a
+ * cudaStream_t (NULL = the handle's own stream); the call is asynchronous w.r.t. that stream when
+ * a stream is given, and synchronises when NULL. Used for device-resident timing and to hand the
+ * rows to a collective (NCCL gather of row bands). */
+int rr_render_rgb8_device(rr_scene *scene, const rr_frame_params *params, void *d_out,
+                          size_t row_stride, void *cuda_stream);
+int rr_render_f32_device(rr_scene *scene, const rr_frame_params *params, void *d_out_rgb,
+                         void *cuda_stream);
+
+/* Instrumented render: same arithmetic, additionally counts rays per class on the device.
+ * Slower; never used for timing. `out` may be NULL (counts only). */
+int rr_render_count(rr_scene *scene, const rr_frame_params *params, uint8_t *out, size_t row_stride,
+                    rr_ray_counts *counts);
+
+/* Un-interleave row bands gathered from `band_count` shards (each packed as rr_render_*_device
+ * wrote them, shard s at d_packed + s*shard_stride_bytes) into a row-major frame, on the device. */
+int rr_bands_unpack_device(const rr_frame_params *params, const void *d_packed,
+                           size_t shard_stride_bytes, void *d_frame, void *cuda_stream);
+
+/* Pinned host memory for frame buffers (full-speed D2H). Plain malloc'd buffers also work. */
+int rr_host_alloc(size_t bytes, void **out);
+int rr_host_free(void *ptr);
+
+/* Average device time in milliseconds of the kernel(s) of the last rr_render_* call on this
+ * handle that was issued on the handle's own stream (CUDA events around the launches). */
+int rr_last_kernel_ms(rr_scene *scene, float *ms);
+
+/* FP32 pipe calibration used for the roofline denominator: runs an unfused FMUL+FADD chain and an
+ * FFMA chain on every SM and reports achieved TFLOP/s. */
+int rr_fp32_peak_tflops(int device, float *unfused_tflops, float *ffma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RR_FFI_H */

@@ -1,0 +1,439 @@
+// rr_ffi.cu — implementation of the C ABI declared in include/rr_ffi.h.
+//
+// Host side of the boundary: validates the POD scene, flattens RenderEnv.objects/materials
+// (render.rs:658-659) into the SoA device layout of rr_device.cuh, owns the per-handle stream and
+// buffers, launches the kernels and moves the frame to the caller. No CPU rendering path exists
+// here: every render entry point either runs the CUDA kernels or fails.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rr_ffi.h"
+#include "rr_kernels.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char *what) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    cudaGetLastError();  // clear sticky-free errors
+    return fail(e == cudaErrorMemoryAllocation ? RR_ERR_OOM : RR_ERR_CUDA, buf);
+}
+#define CU(call)                                           \
+    do {                                                   \
+        cudaError_t e__ = (call);                          \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+    } while (0)
+
+}  // namespace
+
+struct rr_scene {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    rr::DevScene G{};
+    rr::LaunchInfo li{};
+    std::vector<void *> allocs;
+    std::mutex mu;
+    void *d_out = nullptr;
+    size_t d_out_cap = 0;
+    rr::Counters *d_cnt = nullptr;
+    unsigned *d_work = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t chunk_ev[8] = {};
+    float last_ms = 0.0f;
+    bool timed = false;
+};
+
+namespace {
+
+template <typename T>
+int upload(rr_scene *s, const std::vector<T> &h, const T **out) {
+    void *d = nullptr;
+    const size_t bytes = (h.empty() ? 1 : h.size()) * sizeof(T);
+    CU(cudaMalloc(&d, bytes));
+    s->allocs.push_back(d);
+    if (!h.empty()) CU(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const T *>(d);
+    return RR_OK;
+}
+
+int32_t rows_of(const rr_frame_params *p) {
+    const int cnt = p->band_count <= 1 ? 1 : p->band_count;
+    if (cnt == 1) return p->yres;
+    const int br = p->band_rows <= 0 ? 1 : p->band_rows;
+    // bands b = band_index, band_index+cnt, ...; each has br rows except a clipped last one
+    int64_t rows = 0;
+    for (int64_t b = p->band_index; b * br < p->yres; b += cnt) {
+        int64_t lo = b * br, hi = lo + br;
+        if (hi > p->yres) hi = p->yres;
+        rows += hi - lo;
+    }
+    return (int32_t)rows;
+}
+
+int check_params(const rr_frame_params *p) {
+    if (!p) return fail(RR_ERR_BAD_ARG, "params is null");
+    if (p->xres < 0 || p->yres < 0) return fail(RR_ERR_BAD_ARG, "negative resolution");
+    if ((int64_t)p->xres * (int64_t)p->yres > (int64_t)1 << 31) return fail(RR_ERR_BAD_ARG, "frame larger than 2^31 pixels");
+    if (p->band_count > 1 && (p->band_index < 0 || p->band_index >= p->band_count || p->band_rows <= 0))
+        return fail(RR_ERR_BAD_ARG, "bad row-band parameters");
+    if (p->bg_kind != RR_BG_BGCOLOR && p->bg_kind != RR_BG_BLACK) return fail(RR_ERR_BAD_ARG, "unknown bg_kind");
+    if (p->max_refractions > rr::RR_MAX_STACK_HOST)
+        return fail(RR_ERR_UNSUPPORTED, "max_refractions above the device recursion stack (32)");
+    return RR_OK;
+}
+
+rr::FrameParams to_dev(const rr_frame_params *p) {
+    rr::FrameParams d{};
+    d.xres = p->xres; d.yres = p->yres; d.xfov = p->xfov; d.yfov = p->yfov;
+    for (int k = 0; k < 3; ++k) { d.cam_pos[k] = p->cam_position[k]; d.light[k] = p->light[k]; }
+    for (int k = 0; k < 4; ++k) d.cam_rot[k] = p->cam_rotation[k];
+    d.use_raymarching = p->use_raymarching; d.glow_enabled = p->glow_enabled; d.glow_effect = p->glow_effect;
+    d.max_reflections = p->max_reflections; d.max_refractions = p->max_refractions;
+    d.bg_kind = p->bg_kind;
+    d.band_count = p->band_count <= 1 ? 1 : p->band_count;
+    d.band_rows = p->band_rows <= 0 ? 1 : p->band_rows;
+    d.band_index = d.band_count == 1 ? 0 : p->band_index;
+    d.local_rows = rows_of(p);
+    d.row0 = 0;
+    return d;
+}
+
+int launch(rr_scene *s, const rr::FrameParams &P, void *d_out, size_t row_stride, bool f32, rr::Counters *d_cnt,
+           cudaStream_t st) {
+    cudaError_t e = P.use_raymarching ? rr::launch_march(s->G, P, d_out, row_stride, f32, d_cnt, s->d_work, st, s->li)
+                                      : rr::launch_trace(s->G, P, d_out, row_stride, f32, d_cnt, st, s->li);
+    if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
+    return RR_OK;
+}
+
+int ensure_out(rr_scene *s, size_t bytes) {
+    if (bytes <= s->d_out_cap) return RR_OK;
+    if (s->d_out) cudaFree(s->d_out);
+    s->d_out = nullptr;
+    s->d_out_cap = 0;
+    CU(cudaMalloc(&s->d_out, bytes));
+    s->d_out_cap = bytes;
+    return RR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rr_abi_version(void) { return RR_ABI_VERSION; }
+
+const char *rr_last_error(void) { return g_last_error.c_str(); }
+
+int rr_device_count(int *count) {
+    if (!count) return fail(RR_ERR_BAD_ARG, "count is null");
+    CU(cudaGetDeviceCount(count));
+    return RR_OK;
+}
+
+int rr_scene_destroy(rr_scene *s) {
+    if (!s) return RR_OK;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+    for (void *p : s->allocs) cudaFree(p);
+    if (s->d_out) cudaFree(s->d_out);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    for (auto &e : s->chunk_ev) if (e) cudaEventDestroy(e);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    delete s;
+    return RR_OK;
+}
+
+int rr_scene_create(const rr_scene_desc *desc, int device, rr_scene **out) {
+    if (!desc || !out) return fail(RR_ERR_BAD_ARG, "desc/out is null");
+    *out = nullptr;
+    if (desc->n_objects && !desc->objects) return fail(RR_ERR_BAD_ARG, "objects is null");
+    if (desc->n_materials && !desc->materials) return fail(RR_ERR_BAD_ARG, "materials is null");
+    if (desc->n_textures && !desc->textures) return fail(RR_ERR_BAD_ARG, "textures is null");
+    // validate indices and enums before touching the device
+    for (uint32_t i = 0; i < desc->n_materials; ++i) {
+        const rr_material &m = desc->materials[i];
+        if (m.pattern < RR_SOLID || m.pattern > RR_REPEATED_GRADATION) return fail(RR_ERR_BAD_ARG, "unknown pattern");
+        if (m.texture_filter != RR_NEAREST && m.texture_filter != RR_BILINEAR) return fail(RR_ERR_BAD_ARG, "unknown texture_filter");
+        if (m.texture >= 0 && (uint32_t)m.texture >= desc->n_textures) return fail(RR_ERR_BAD_ARG, "texture index out of range");
+    }
+    for (uint32_t i = 0; i < desc->n_textures; ++i) {
+        const rr_texture &t = desc->textures[i];
+        if (!t.rgb8 || t.width == 0 || t.height == 0) return fail(RR_ERR_BAD_ARG, "empty texture");
+    }
+    for (uint32_t i = 0; i < desc->n_objects; ++i) {
+        const rr_object &o = desc->objects[i];
+        if (o.kind != RR_SPHERE && o.kind != RR_FLOOR) return fail(RR_ERR_BAD_ARG, "unknown object kind");
+        if (o.uvmap < RR_UV_XY || o.uvmap > RR_UV_LL) return fail(RR_ERR_BAD_ARG, "unknown uvmap");
+        if (o.material < 0 || (uint32_t)o.material >= desc->n_materials) return fail(RR_ERR_BAD_ARG, "material index out of range");
+    }
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(RR_ERR_BAD_ARG, "device index out of range");
+    CU(cudaSetDevice(device));
+
+    rr_scene *s = new (std::nothrow) rr_scene();
+    if (!s) return fail(RR_ERR_OOM, "host allocation failed");
+    s->device = device;
+    int rc = RR_OK;
+    auto bail = [&](int code) { rr_scene_destroy(s); return code; };
+
+    std::vector<float4> sph, sph_m, flo_o, flo_n, obj_a, obj_n;
+    std::vector<float> sph_glow;
+    std::vector<int> sph_oi, flo_oi;
+    std::vector<int4> obj_b;
+    int n_glow = 0;
+    for (uint32_t i = 0; i < desc->n_objects; ++i) {
+        const rr_object &o = desc->objects[i];
+        const rr_material &m = desc->materials[o.material];
+        if (m.glow_dist != 0.0f) n_glow++;
+        obj_a.push_back(make_float4(o.org[0], o.org[1], o.org[2], o.r));
+        obj_n.push_back(make_float4(o.face_normal[0], o.face_normal[1], o.face_normal[2], 0.0f));
+        obj_b.push_back(make_int4(o.kind, o.uvmap, o.material, 0));
+        if (o.kind == RR_SPHERE) {
+            const float rr2 = o.r * o.r;  // the single f32 product of render.rs:456
+            sph.push_back(make_float4(o.org[0], o.org[1], o.org[2], rr2));
+            sph_m.push_back(make_float4(o.org[0], o.org[1], o.org[2], o.r));
+            sph_glow.push_back(m.glow_dist);
+            sph_oi.push_back((int)i);
+        } else {
+            flo_o.push_back(make_float4(o.org[0], o.org[1], o.org[2], m.glow_dist));
+            flo_n.push_back(make_float4(o.face_normal[0], o.face_normal[1], o.face_normal[2], 0.0f));
+            flo_oi.push_back((int)i);
+        }
+    }
+    std::vector<rr::DevTexture> tex;
+    for (uint32_t i = 0; i < desc->n_textures; ++i) {
+        const rr_texture &t = desc->textures[i];
+        std::vector<uint8_t> px(t.rgb8, t.rgb8 + (size_t)t.width * t.height * 3);
+        const uint8_t *d = nullptr;
+        if ((rc = upload(s, px, &d)) != RR_OK) return bail(rc);
+        tex.push_back(rr::DevTexture{d, t.width, t.height});
+    }
+    std::vector<rr::DevMaterial> mats;
+    for (uint32_t i = 0; i < desc->n_materials; ++i) {
+        const rr_material &m = desc->materials[i];
+        rr::DevMaterial d{};
+        for (int k = 0; k < 3; ++k) { d.diffuse[k] = m.diffuse[k]; d.specular[k] = m.specular[k]; }
+        d.pn = m.pn; d.t = m.t; d.n = m.n; d.glow_dist = m.glow_dist;
+        d.pattern = m.pattern; d.pattern_scale = m.pattern_scale; d.pattern_angle_scale = m.pattern_angle_scale;
+        d.texture = m.texture; d.texture_filter = m.texture_filter;
+        mats.push_back(d);
+    }
+    rr::DevScene &G = s->G;
+    G.n_spheres = (int)sph.size(); G.n_floors = (int)flo_o.size();
+    G.n_objects = (int)desc->n_objects; G.n_materials = (int)desc->n_materials; G.n_glow = n_glow;
+    if ((rc = upload(s, sph, &G.sph)) || (rc = upload(s, sph_m, &G.sph_m)) || (rc = upload(s, sph_glow, &G.sph_glow)) ||
+        (rc = upload(s, sph_oi, &G.sph_oi)) || (rc = upload(s, flo_o, &G.flo_o)) || (rc = upload(s, flo_n, &G.flo_n)) ||
+        (rc = upload(s, flo_oi, &G.flo_oi)) || (rc = upload(s, obj_a, &G.obj_a)) || (rc = upload(s, obj_n, &G.obj_n)) ||
+        (rc = upload(s, obj_b, &G.obj_b)) || (rc = upload(s, mats, &G.mat)) || (rc = upload(s, tex, &G.tex)))
+        return bail(rc);
+
+    cudaError_t e;
+    int sm = 0, optin = 0;
+    if ((e = cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&s->ev0)) != cudaSuccess || (e = cudaEventCreate(&s->ev1)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&s->d_cnt), sizeof(rr::Counters))) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&s->d_work), 64)) != cudaSuccess)
+        return bail(fail_cuda(e, "rr_scene_create"));
+    s->allocs.push_back(s->d_cnt);
+    s->allocs.push_back(s->d_work);
+    for (auto &ev : s->chunk_ev)
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
+    s->li.sm_count = sm;
+    s->li.smem_optin = (size_t)optin;
+    *out = s;
+    return RR_OK;
+}
+
+int rr_frame_rows(const rr_frame_params *params, int32_t *rows_out) {
+    if (!rows_out) return fail(RR_ERR_BAD_ARG, "rows_out is null");
+    int rc = check_params(params);
+    if (rc) return rc;
+    *rows_out = rows_of(params);
+    return RR_OK;
+}
+
+int rr_render_rgb8_device(rr_scene *s, const rr_frame_params *params, void *d_out, size_t row_stride, void *cuda_stream) {
+    if (!s || !d_out) return fail(RR_ERR_BAD_ARG, "scene/d_out is null");
+    int rc = check_params(params);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->device));
+    rr::FrameParams P = to_dev(params);
+    if (row_stride == 0) row_stride = (size_t)P.xres * 3;
+    if (row_stride < (size_t)P.xres * 3) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
+    if (cuda_stream) return launch(s, P, d_out, row_stride, false, nullptr, reinterpret_cast<cudaStream_t>(cuda_stream));
+    CU(cudaEventRecord(s->ev0, s->stream));
+    if ((rc = launch(s, P, d_out, row_stride, false, nullptr, s->stream))) return rc;
+    CU(cudaEventRecord(s->ev1, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+    s->timed = true;
+    return RR_OK;
+}
+
+int rr_render_f32_device(rr_scene *s, const rr_frame_params *params, void *d_out, void *cuda_stream) {
+    if (!s || !d_out) return fail(RR_ERR_BAD_ARG, "scene/d_out is null");
+    int rc = check_params(params);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->device));
+    rr::FrameParams P = to_dev(params);
+    if (cuda_stream) return launch(s, P, d_out, 0, true, nullptr, reinterpret_cast<cudaStream_t>(cuda_stream));
+    CU(cudaEventRecord(s->ev0, s->stream));
+    if ((rc = launch(s, P, d_out, 0, true, nullptr, s->stream))) return rc;
+    CU(cudaEventRecord(s->ev1, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+    s->timed = true;
+    return RR_OK;
+}
+
+// Frame to host memory. The frame is rendered in up to 8 row chunks on the handle's stream; each
+// chunk's device-to-host copy is queued on a second stream as soon as its kernel finishes, so the
+// PCIe transfer of chunk k overlaps the kernel of chunk k+1 (the copy is the longer leg at 4K/8K).
+int rr_render_rgb8(rr_scene *s, const rr_frame_params *params, uint8_t *out, size_t row_stride) {
+    if (!s || !out) return fail(RR_ERR_BAD_ARG, "scene/out is null");
+    int rc = check_params(params);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->device));
+    rr::FrameParams P = to_dev(params);
+    const size_t packed = (size_t)P.xres * 3;
+    if (row_stride == 0) row_stride = packed;
+    if (row_stride < packed) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
+    const int rows = P.local_rows;
+    if (rows == 0 || P.xres == 0) return RR_OK;
+    if ((rc = ensure_out(s, packed * rows))) return rc;
+    int nchunk = (int)((packed * rows) / (4u << 20));  // ~4 MiB per chunk, at most 8 chunks
+    if (nchunk < 1) nchunk = 1;
+    if (nchunk > 8) nchunk = 8;
+    int chunk_rows = (rows + nchunk - 1) / nchunk;
+    chunk_rows = (chunk_rows + 3) & ~3;  // whole 4-row tiles
+    CU(cudaEventRecord(s->ev0, s->stream));
+    int k = 0;
+    for (int r0 = 0; r0 < rows; r0 += chunk_rows, ++k) {
+        rr::FrameParams C = P;
+        C.row0 = r0;
+        C.local_rows = (rows - r0 < chunk_rows) ? rows - r0 : chunk_rows;
+        uint8_t *d = reinterpret_cast<uint8_t *>(s->d_out) + (size_t)r0 * packed;
+        if ((rc = launch(s, C, d, packed, false, nullptr, s->stream))) return rc;
+        CU(cudaEventRecord(s->chunk_ev[k], s->stream));
+        CU(cudaStreamWaitEvent(s->copy_stream, s->chunk_ev[k], 0));
+        CU(cudaMemcpy2DAsync(out + (size_t)r0 * row_stride, row_stride, d, packed, packed, (size_t)C.local_rows,
+                             cudaMemcpyDeviceToHost, s->copy_stream));
+    }
+    CU(cudaEventRecord(s->ev1, s->stream));
+    CU(cudaStreamSynchronize(s->copy_stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+    s->timed = true;
+    return RR_OK;
+}
+
+int rr_render_f32(rr_scene *s, const rr_frame_params *params, float *out_rgb) {
+    if (!s || !out_rgb) return fail(RR_ERR_BAD_ARG, "scene/out is null");
+    int rc = check_params(params);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->device));
+    rr::FrameParams P = to_dev(params);
+    const size_t bytes = (size_t)P.xres * P.local_rows * 3 * sizeof(float);
+    if (bytes == 0) return RR_OK;
+    if ((rc = ensure_out(s, bytes))) return rc;
+    CU(cudaEventRecord(s->ev0, s->stream));
+    if ((rc = launch(s, P, s->d_out, 0, true, nullptr, s->stream))) return rc;
+    CU(cudaEventRecord(s->ev1, s->stream));
+    CU(cudaMemcpyAsync(out_rgb, s->d_out, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+    s->timed = true;
+    return RR_OK;
+}
+
+int rr_render_count(rr_scene *s, const rr_frame_params *params, uint8_t *out, size_t row_stride, rr_ray_counts *counts) {
+    if (!s || !counts) return fail(RR_ERR_BAD_ARG, "scene/counts is null");
+    int rc = check_params(params);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->device));
+    rr::FrameParams P = to_dev(params);
+    const size_t packed = (size_t)P.xres * 3;
+    if (row_stride == 0) row_stride = packed;
+    if (row_stride < packed) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
+    std::memset(counts, 0, sizeof(*counts));
+    if (P.local_rows == 0 || P.xres == 0) return RR_OK;
+    if ((rc = ensure_out(s, packed * P.local_rows))) return rc;
+    CU(cudaMemsetAsync(s->d_cnt, 0, sizeof(rr::Counters), s->stream));
+    if ((rc = launch(s, P, s->d_out, packed, false, s->d_cnt, s->stream))) return rc;
+    rr::Counters h{};
+    CU(cudaMemcpyAsync(&h, s->d_cnt, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+    if (out)
+        CU(cudaMemcpy2DAsync(out, row_stride, s->d_out, packed, packed, (size_t)P.local_rows, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    counts->pixels = h.pixels; counts->primary = h.primary; counts->reflect = h.reflect; counts->refract = h.refract;
+    counts->shadow = h.shadow; counts->object_tests = h.object_tests; counts->march_steps = h.march_steps;
+    counts->bg_evals = h.bg_evals;
+    return RR_OK;
+}
+
+int rr_bands_unpack_device(const rr_frame_params *params, const void *d_packed, size_t shard_stride_bytes, void *d_frame,
+                           void *cuda_stream) {
+    if (!d_packed || !d_frame) return fail(RR_ERR_BAD_ARG, "null device pointer");
+    int rc = check_params(params);
+    if (rc) return rc;
+    rr::FrameParams P = to_dev(params);
+    cudaError_t e = rr::launch_bands_unpack(P, d_packed, shard_stride_bytes, d_frame, reinterpret_cast<cudaStream_t>(cuda_stream));
+    if (e != cudaSuccess) return fail_cuda(e, "bands_unpack");
+    if (!cuda_stream) CU(cudaStreamSynchronize(nullptr));
+    return RR_OK;
+}
+
+int rr_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(RR_ERR_BAD_ARG, "out is null");
+    *out = nullptr;
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return RR_OK;
+}
+
+int rr_host_free(void *ptr) {
+    if (!ptr) return RR_OK;
+    CU(cudaFreeHost(ptr));
+    return RR_OK;
+}
+
+int rr_last_kernel_ms(rr_scene *s, float *ms) {
+    if (!s || !ms) return fail(RR_ERR_BAD_ARG, "scene/ms is null");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (!s->timed) return fail(RR_ERR_BAD_ARG, "no timed render on this handle yet");
+    *ms = s->last_ms;
+    return RR_OK;
+}
+
+int rr_fp32_peak_tflops(int device, float *unfused_tflops, float *ffma_tflops) {
+    if (!unfused_tflops || !ffma_tflops) return fail(RR_ERR_BAD_ARG, "null output");
+    cudaError_t e = rr::fp32_peak(device, unfused_tflops, ffma_tflops);
+    if (e != cudaSuccess) return fail_cuda(e, "fp32_peak");
+    return RR_OK;
+}
+
+}  // extern "C"

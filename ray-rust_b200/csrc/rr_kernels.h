@@ -1,0 +1,33 @@
+// rr_kernels.h — host-callable launchers of the sm_100a kernels (implemented in rr_trace.cu,
+// rr_march.cu, rr_util.cu). Internal to libray_rust_b200.so; the public surface is include/rr_ffi.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "rr_device.cuh"
+
+namespace rr {
+
+constexpr int RR_MAX_STACK_HOST = 32;  // == RR_MAX_STACK / RR_MARCH_MAX_STACK in the kernels
+
+struct LaunchInfo {
+    int sm_count;
+    size_t smem_optin;  // max opt-in dynamic shared memory per block
+};
+
+// bytes of dynamic shared memory needed to stage the intersection lists of `G`
+size_t scene_smem_bytes(const DevScene &G);
+
+// Ray-trace mode. d_out: RGB8 (row_stride bytes per row) or, when f32_out, packed float rgb.
+// d_cnt != nullptr selects the instrumented instantiation.
+cudaError_t launch_trace(const DevScene &G, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
+                         Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li);
+// Ray-march mode (same contract). d_work: one unsigned int work counter (zeroed by the launcher).
+cudaError_t launch_march(const DevScene &G, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
+                         Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li);
+// Row-band un-interleave (multi-GPU gather epilogue).
+cudaError_t launch_bands_unpack(const FrameParams &P, const void *d_packed, size_t shard_stride, void *d_frame,
+                                cudaStream_t stream);
+// FP32 pipe calibration (roofline denominator): achieved TFLOP/s of unfused FMUL+FADD and of FFMA.
+cudaError_t fp32_peak(int device, float *unfused_tflops, float *ffma_tflops);
+
+}  // namespace rr

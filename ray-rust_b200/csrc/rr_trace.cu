@@ -1,0 +1,136 @@
+// rr_trace.cu — ray-trace kernel for sm_100a (render.rs:806-827 + :993-1224, fused with the
+// putpoint quantiser of main.rs:148-152).
+//
+// Mapping: a warp owns an 8x4 pixel tile (coherent primary rays, 24-byte row runs for the RGB8
+// store); warps walk the tile list with a static grid stride from a persistent grid of
+// (SM count x resident blocks), so the scene is staged into shared memory once per block.
+// The kernel is FP32-ALU / divergence bound: compiled with -fmad=false for bit parity, no tensor
+// cores, DRAM traffic = the framebuffer store only.
+#include "rr_kernels.h"
+#include "rr_trace.cuh"
+
+namespace rr {
+
+constexpr int TRACE_THREADS = 256;
+
+__device__ __forceinline__ SceneView stage_scene(const DevScene &G, float4 *smem, bool stage) {
+    SceneView S;
+    S.n_spheres = G.n_spheres;
+    S.n_floors = G.n_floors;
+    if (!stage) {
+        S.sph = G.sph; S.sph_oi = G.sph_oi; S.flo_o = G.flo_o; S.flo_n = G.flo_n; S.flo_oi = G.flo_oi;
+        return S;
+    }
+    float4 *sph = smem;
+    float4 *flo_o = sph + G.n_spheres;
+    float4 *flo_n = flo_o + G.n_floors;
+    int *sph_oi = reinterpret_cast<int *>(flo_n + G.n_floors);
+    int *flo_oi = sph_oi + G.n_spheres;
+    for (int i = threadIdx.x; i < G.n_spheres; i += blockDim.x) {
+        sph[i] = G.sph[i];
+        sph_oi[i] = G.sph_oi[i];
+    }
+    for (int i = threadIdx.x; i < G.n_floors; i += blockDim.x) {
+        flo_o[i] = G.flo_o[i];
+        flo_n[i] = G.flo_n[i];
+        flo_oi[i] = G.flo_oi[i];
+    }
+    __syncthreads();
+    S.sph = sph; S.sph_oi = sph_oi; S.flo_o = flo_o; S.flo_n = flo_n; S.flo_oi = flo_oi;
+    return S;
+}
+
+__device__ __forceinline__ void flush_counters(const Counters &c, Counters *g) {
+    unsigned long long v[8] = {c.pixels, c.primary, c.reflect, c.refract, c.shadow, c.object_tests, c.march_steps, c.bg_evals};
+    unsigned long long *gp = reinterpret_cast<unsigned long long *>(g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        unsigned long long x = v[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(&gp[k], x);
+    }
+}
+
+template <bool COUNT, bool F32OUT, bool STAGE>
+__global__ void __launch_bounds__(TRACE_THREADS)
+trace_kernel(const DevScene G, const FrameParams P, void *__restrict__ out, size_t row_stride, Counters *gcnt,
+             int fast_store) {
+    extern __shared__ float4 rr_smem[];
+    const SceneView S = stage_scene(G, rr_smem, STAGE);
+
+    const int W = P.xres, rows = P.local_rows;
+    const int tiles_x = (W + 7) >> 3, tiles_y = (rows + 3) >> 2;
+    const int ntiles = tiles_x * tiles_y;
+    const int lane = threadIdx.x & 31;
+    const int col = lane & 7, row = lane >> 3;
+    const int warps_per_block = blockDim.x >> 5;
+    const int gw = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int nw = gridDim.x * warps_per_block;
+    Counters cnt = {};
+
+    for (int tile = gw; tile < ntiles; tile += nw) {
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int x0 = tx << 3, ly0 = ty << 2;
+        const int ix = x0 + col, ly = ly0 + row;
+        const bool valid = ix < W && ly < rows;
+        V3 c = mk(0.0f, 0.0f, 0.0f);
+        if (valid) c = trace_pixel<COUNT>(G, S, P, ix, local_to_image_row(P, ly), cnt);
+        if (F32OUT) {
+            if (valid) {
+                float *o = reinterpret_cast<float *>(out) + ((size_t)ly * W + ix) * 3;
+                o[0] = c.x; o[1] = c.y; o[2] = c.z;
+            }
+        } else {
+            const unsigned rgb = quantize(c.x) | (quantize(c.y) << 8) | (quantize(c.z) << 16);
+            store_tile_rgb8(reinterpret_cast<uint8_t *>(out), row_stride, x0, ly0, W, rows, rgb, fast_store != 0);
+        }
+    }
+    if (COUNT) flush_counters(cnt, gcnt);
+}
+
+size_t scene_smem_bytes(const DevScene &G) {
+    return (size_t)G.n_spheres * (sizeof(float4) + sizeof(int)) + (size_t)G.n_floors * (2 * sizeof(float4) + sizeof(int)) + 16;
+}
+
+template <bool COUNT, bool F32OUT, bool STAGE>
+static cudaError_t launch_one(const DevScene &G, const FrameParams &P, void *d_out, size_t row_stride, Counters *d_cnt,
+                              cudaStream_t stream, const LaunchInfo &li, size_t smem) {
+    auto kern = trace_kernel<COUNT, F32OUT, STAGE>;
+    cudaError_t e;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TRACE_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const int tiles = ((P.xres + 7) / 8) * ((P.local_rows + 3) / 4);
+    const int need = (tiles + (TRACE_THREADS / 32) - 1) / (TRACE_THREADS / 32);
+    int grid = li.sm_count * per_sm;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    const int fast = (!F32OUT && (P.xres % 8 == 0) && (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0)) ? 1 : 0;
+    kern<<<grid, TRACE_THREADS, smem, stream>>>(G, P, d_out, row_stride, d_cnt, fast);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace(const DevScene &G, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
+                         Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li) {
+    if (P.xres <= 0 || P.local_rows <= 0) return cudaSuccess;
+    size_t smem = scene_smem_bytes(G);
+    const bool stage = smem <= li.smem_optin / 2;  // keep >= 2 blocks per SM resident
+    if (!stage) smem = 0;
+    if (d_cnt) {
+        if (f32_out) return stage ? launch_one<true, true, true>(G, P, d_out, row_stride, d_cnt, stream, li, smem)
+                                  : launch_one<true, true, false>(G, P, d_out, row_stride, d_cnt, stream, li, smem);
+        return stage ? launch_one<true, false, true>(G, P, d_out, row_stride, d_cnt, stream, li, smem)
+                     : launch_one<true, false, false>(G, P, d_out, row_stride, d_cnt, stream, li, smem);
+    }
+    if (f32_out) return stage ? launch_one<false, true, true>(G, P, d_out, row_stride, d_cnt, stream, li, smem)
+                              : launch_one<false, true, false>(G, P, d_out, row_stride, d_cnt, stream, li, smem);
+    return stage ? launch_one<false, false, true>(G, P, d_out, row_stride, d_cnt, stream, li, smem)
+                 : launch_one<false, false, false>(G, P, d_out, row_stride, d_cnt, stream, li, smem);
+}
+
+}  // namespace rr

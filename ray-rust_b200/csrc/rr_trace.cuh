@@ -1,0 +1,255 @@
+// rr_trace.cuh — ray-trace mode of the per-pixel path (render.rs:993-1224) as device functions.
+//
+// Design (DESIGN.md "trace kernel"):
+//   * scene-level raycast() is a brute-force loop like the reference's, but over two homogeneous
+//     SoA lists (floors, then spheres) staged in shared memory, so the inner loop has no per-object
+//     kind dispatch. Ties are resolved to the lowest ORIGINAL object index, which is what the
+//     reference's in-order strict `<` scan does (appendix A Q6).
+//   * the refraction recursion shading()->raytrace() (render.rs:1093-1115) is unrolled into an
+//     explicit per-thread stack of suspended parent frames; evaluation order of every float sum
+//     is unchanged (the child colour is complete before the parent blends it).
+#pragma once
+#include "rr_device.cuh"
+
+namespace rr {
+
+// pointers to the intersection lists the hot loops read (shared memory when staged)
+struct SceneView {
+    const float4 *sph;
+    const int *sph_oi;
+    const float4 *flo_o;
+    const float4 *flo_n;
+    const int *flo_oi;
+    int n_spheres, n_floors;
+};
+
+struct Hit {
+    float t;
+    int idx;
+};
+
+// RenderFloor::raycast (render.rs:557-569) + RenderSphere::raycast (render.rs:447-471) inside the
+// scene loop of render.rs:993-1018.
+//
+// Sphere algebra: the reference forms b = 2*(eye.wpt), c = wpt.wpt - r*r, d2 = b*b - 4*c,
+// d = sqrt(d2), t0 = (-b - d)/2, t1 = t0 + d. With D = eye.wpt and q = D*D - c this is, exactly
+// (scalings by 2 and 4 commute with IEEE rounding): d2 = 4q, d = 2*sqrt(q), t0 = -D - sqrt(q),
+// t1 = t0 + 2*sqrt(q), and `d2 >= EPSILON` <=> `q >= EPSILON/4`. Same bits, fewer multiplies.
+__device__ __forceinline__ Hit raycast(const SceneView &S, const V3 &vi, const V3 &eye, int ig, unsigned flags) {
+    float t = RR_INF;
+    int idx = 0;
+    for (int f = 0; f < S.n_floors; ++f) {
+        const int oi = S.flo_oi[f];
+        if (oi == ig) continue;
+        const float4 o = S.flo_o[f];
+        const float4 n4 = S.flo_n[f];
+        const V3 n = mk(n4.x, n4.y, n4.z);
+        const V3 wpt = vi - mk(o.x, o.y, o.z);
+        const float w = dot(n, eye);
+        if (w <= 0.0f) {
+            const float t0 = (-dot(n, wpt)) / w;
+            if (t0 >= 0.0f && t0 < t) {  // floors are scanned in index order: strict <
+                t = t0;
+                idx = oi;
+            }
+        }
+    }
+    const bool near_ok = (flags & OUTONLY) == 0;
+    const bool far_ok = (flags & INONLY) == 0;
+    for (int s = 0; s < S.n_spheres; ++s) {
+        const float4 c4 = S.sph[s];
+        const V3 wpt = vi - mk(c4.x, c4.y, c4.z);
+        const float D = dot(eye, wpt);
+        const float c = dot(wpt, wpt) - c4.w;
+        const float q = D * D - c;
+        if (q >= F32_EPS_QUARTER) {
+            const float sq = sqrtf(q);
+            const float t0 = -D - sq;
+            float cand = RR_INF;
+            if (near_ok && t0 >= 0.0f) {
+                cand = t0;
+            } else if (far_ok) {
+                const float t1 = t0 + 2.0f * sq;
+                if (0.0f < t1) cand = t1;
+            }
+            if (cand <= t) {
+                const int oi = S.sph_oi[s];
+                // lowest original index wins exact ties (floors were scanned first)
+                if (oi != ig && (cand < t || (cand < RR_INF && oi < idx))) {
+                    t = cand;
+                    idx = oi;
+                }
+            }
+        }
+    }
+    return Hit{t, idx};
+}
+
+// get_normal — render.rs:443-445 (sphere), :553-555 (floor)
+__device__ __forceinline__ V3 object_normal(const DevScene &G, int idx, const V3 &pt, const float4 &a, int kind) {
+    if (kind == 0) return normalized(pt - mk(a.x, a.y, a.z));
+    const float4 n = __ldg(&G.obj_n[idx]);
+    return mk(n.x, n.y, n.z);
+}
+
+struct TraceFrame {  // a suspended raytrace() frame waiting for its refraction child
+    float ret[3];
+    float fcs[3];   // fcs before this hit was accumulated
+    float A[3];     // (kd*k1 + k2) * (1 - f)
+    float f;
+    float vi[3];    // continuation ray (valid when cont)
+    float eye[3];
+    int ig;         // object that was hit (== ig of the continuation)
+    int lev;
+    unsigned flags; // continuation flags
+    int cont;       // will the parent's bounce loop continue after this hit?
+};
+
+constexpr int RR_MAX_STACK = 32;  // >= max_refractions (checked on the host)
+
+template <bool COUNT>
+__device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneView &S, const FrameParams &P, int ix, int iy,
+                                          Counters &cnt) {
+    const V3 light = mk(P.light[0], P.light[1], P.light[2]);
+    V3 vi = mk(P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]);
+    V3 eye = primary_ray(P, ix, iy);
+    int lev = 0, ig = -1, depth = 0;
+    unsigned flags = 0;
+    V3 ret = mk(0.0f, 0.0f, 0.0f), fcs = mk(1.0f, 1.0f, 1.0f);
+    TraceFrame stack[RR_MAX_STACK];
+    int ray_class = 0;  // 0 primary, 1 refract child's first ray, 2 reflect continuation
+    if (COUNT) cnt.pixels++;
+
+    for (;;) {
+        lev += 1;  // render.rs:1157
+        if (COUNT) {
+            if (ray_class == 0) cnt.primary++;
+            else if (ray_class == 1) cnt.refract++;
+            else cnt.reflect++;
+            cnt.object_tests += (unsigned long long)(G.n_objects - (ig >= 0 ? 1 : 0));
+        }
+        const Hit h = raycast(S, vi, eye, ig, flags);
+        bool frame_done;
+        if (h.t < RR_INF) {
+            const int idx = h.idx;
+            const V3 pt = (eye * h.t) + vi;  // render.rs:1164
+            const float4 oa = __ldg(&G.obj_a[idx]);
+            const int4 ob = __ldg(&G.obj_b[idx]);
+            const V3 n = object_normal(G, idx, pt, oa, ob.x);
+            const DevMaterial &m = G.mat[ob.z];
+
+            // ---- shading(), render.rs:1020-1140 ----
+            const float light_incidence = dot(light, n);
+            const float ln2 = 2.0f * light_incidence;
+            const V3 rr_light = (n * ln2) - light;
+            const int pn = m.pn;
+            const float diffuse_intensity = fmaxf(light_incidence, 0.0f);
+            const V3 shadow_org = pt + (light * F32_EPSILON);
+            float reflection_intensity = 0.0f;
+            if (pn != 0) {
+                const float ri = -dot(rr_light, eye);
+                if (ri > 0.0f) reflection_intensity = rs_powi(ri, pn);
+            }
+            float k1 = 0.2f, k2 = 0.0f;
+            {
+                if (COUNT) {
+                    cnt.shadow++;
+                    cnt.object_tests += (unsigned long long)(G.n_objects - 1);
+                }
+                const Hit sh = raycast(S, shadow_org, light, idx, 0u);
+                bool lit = sh.t >= RR_INF;
+                if (!lit) lit = 0.0f < G.mat[__ldg(&G.obj_b[sh.idx]).z].t;
+                if (lit) {
+                    k1 = fminf(k1 + diffuse_intensity, 1.0f);
+                    k2 = reflection_intensity;
+                }
+            }
+            float u, v;
+            get_uv(m, pt - mk(oa.x, oa.y, oa.z), ob.y, u, v);
+            const V3 kd = lookup_texture(G, m, u, v);
+            V3 face = mk(kd.x * k1 + k2, kd.y * k1 + k2, kd.z * k1 + k2);
+            const V3 ks = mk(m.specular[0], m.specular[1], m.specular[2]);
+
+            if (lev < P.max_refractions && 0.0f < m.t) {
+                // refraction child, render.rs:1093-1115: suspend this frame
+                const float sp = dot(eye, n);
+                const float f = m.t;
+                const float frac = m.n;
+                const float reference = sp * ((sp > 0.0f ? frac : 1.0f / frac) - 1.0f);
+                const V3 ray = normalized(eye + (n * reference));
+                const V3 pt3 = pt + (ray * F32_EPSILON);
+                const float omf = 1.0f - f;
+                TraceFrame &F = stack[depth];
+                F.ret[0] = ret.x; F.ret[1] = ret.y; F.ret[2] = ret.z;
+                F.fcs[0] = fcs.x; F.fcs[1] = fcs.y; F.fcs[2] = fcs.z;
+                F.A[0] = face.x * omf; F.A[1] = face.y * omf; F.A[2] = face.z * omf;
+                F.f = f;
+                F.ig = idx;
+                F.lev = lev;
+                // what the parent does after `ret += face*fcs; fcs *= ks` (render.rs:1175-1211)
+                const V3 nf = mk(fcs.x * ks.x, fcs.y * ks.y, fcs.z * ks.z);
+                const bool cont = !(idx == 0) && !((nf.x + nf.y + nf.z) <= 0.1f) && !(lev >= P.max_reflections);
+                F.cont = cont ? 1 : 0;
+                if (cont) {
+                    const float en2 = -2.0f * dot(eye, n);
+                    const V3 e2 = eye + n * en2;
+                    F.vi[0] = pt.x; F.vi[1] = pt.y; F.vi[2] = pt.z;
+                    F.eye[0] = e2.x; F.eye[1] = e2.y; F.eye[2] = e2.z;
+                    F.flags = dot(n, e2) < 0.0f ? OUTONLY : INONLY;
+                }
+                depth += 1;
+                vi = pt3;
+                eye = ray;
+                ig = idx;
+                flags = sp < 0.0f ? OUTONLY : INONLY;
+                ret = mk(0.0f, 0.0f, 0.0f);
+                fcs = mk(1.0f, 1.0f, 1.0f);
+                ray_class = 1;
+                continue;  // child starts with lev = nest; the loop head increments it
+            }
+
+            // ---- back in raytrace(), render.rs:1173-1211 ----
+            ret = mk(ret.x + face.x * fcs.x, ret.y + face.y * fcs.y, ret.z + face.z * fcs.z);
+            fcs = mk(fcs.x * ks.x, fcs.y * ks.y, fcs.z * ks.z);
+            if (idx == 0 || (fcs.x + fcs.y + fcs.z) <= 0.1f || lev >= P.max_reflections) {
+                frame_done = true;
+            } else {
+                vi = pt;
+                const float en2 = -2.0f * dot(eye, n);
+                eye = eye + n * en2;
+                flags = dot(n, eye) < 0.0f ? OUTONLY : INONLY;
+                ig = idx;
+                ray_class = 2;
+                frame_done = false;
+            }
+        } else {
+            if (COUNT) cnt.bg_evals++;
+            const V3 bg = bgcolor(P, eye);  // render.rs:1213-1216
+            ret = mk(ret.x + bg.x * fcs.x, ret.y + bg.y * fcs.y, ret.z + bg.z * fcs.z);
+            frame_done = true;
+        }
+
+        // return from finished frames into their suspended parents (render.rs:1128-1132 then :1175-1211)
+        while (frame_done) {
+            if (depth == 0) return ret;
+            depth -= 1;
+            const TraceFrame &F = stack[depth];
+            const float f = F.f;
+            const V3 face = mk(F.A[0] + ret.x * f, F.A[1] + ret.y * f, F.A[2] + ret.z * f);
+            ret = mk(F.ret[0] + face.x * F.fcs[0], F.ret[1] + face.y * F.fcs[1], F.ret[2] + face.z * F.fcs[2]);
+            if (F.cont) {
+                const DevMaterial &pm = G.mat[__ldg(&G.obj_b[F.ig]).z];
+                fcs = mk(F.fcs[0] * pm.specular[0], F.fcs[1] * pm.specular[1], F.fcs[2] * pm.specular[2]);
+                vi = mk(F.vi[0], F.vi[1], F.vi[2]);
+                eye = mk(F.eye[0], F.eye[1], F.eye[2]);
+                flags = F.flags;
+                ig = F.ig;
+                lev = F.lev;
+                ray_class = 2;
+                frame_done = false;
+            }
+        }
+    }
+}
+
+}  // namespace rr

@@ -1,0 +1,96 @@
+// rr_util.cu — row-band un-interleave kernel and the FP32 pipe calibration micro-benchmark.
+#include "rr_kernels.h"
+
+namespace rr {
+
+// One block per image row: copy the row from the shard that rendered it (packed band order) to its
+// place in the row-major frame. 16-byte vectors when everything is aligned, bytes otherwise.
+__global__ void bands_unpack_kernel(const uint8_t *__restrict__ packed, size_t shard_stride, uint8_t *__restrict__ frame,
+                                    int W, int H, int band_rows, int band_count) {
+    const int iy = blockIdx.x;
+    if (iy >= H) return;
+    const int b = iy / band_rows;
+    const int shard = b % band_count;
+    const int local_row = (b / band_count) * band_rows + (iy - b * band_rows);
+    const size_t row_bytes = (size_t)W * 3;
+    const uint8_t *src = packed + (size_t)shard * shard_stride + (size_t)local_row * row_bytes;
+    uint8_t *dst = frame + (size_t)iy * row_bytes;
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | row_bytes) & 15) == 0) {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        for (size_t i = threadIdx.x; i < row_bytes / 16; i += blockDim.x) d4[i] = s4[i];
+    } else {
+        for (size_t i = threadIdx.x; i < row_bytes; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+cudaError_t launch_bands_unpack(const FrameParams &P, const void *d_packed, size_t shard_stride, void *d_frame,
+                                cudaStream_t stream) {
+    if (P.yres <= 0 || P.xres <= 0) return cudaSuccess;
+    const int br = P.band_rows <= 0 ? 1 : P.band_rows;
+    const int bc = P.band_count <= 1 ? 1 : P.band_count;
+    bands_unpack_kernel<<<P.yres, 256, 0, stream>>>(reinterpret_cast<const uint8_t *>(d_packed), shard_stride,
+                                                   reinterpret_cast<uint8_t *>(d_frame), P.xres, P.yres, br, bc);
+    return cudaGetLastError();
+}
+
+// ---- FP32 pipe calibration -------------------------------------------------------------------
+// 8 independent dependency chains per thread so the 4-cycle FMA-pipe latency is covered at
+// 16 warps/SMSP. FUSED=false compiles (under -fmad=false) to FMUL+FADD pairs: the instruction mix
+// bit-exact parity forces on the render kernels; FUSED=true uses explicit fmaf -> FFMA.
+template <bool FUSED>
+__global__ void __launch_bounds__(256) fp32_chain_kernel(float *out, int iters, float a, float b) {
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (float)(threadIdx.x + k) * 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = FUSED ? __fmaf_rn(x[k], a, b) : (x[k] * a + b);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += x[k];
+    if (s == 123.456f) out[0] = s;  // keep the chains alive
+}
+
+template <bool FUSED>
+static cudaError_t time_chain(int sm_count, float *tflops) {
+    float *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 4);
+    if (e != cudaSuccess) return e;
+    const int iters = 1 << 15, blocks = sm_count * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        fp32_chain_kernel<FUSED><<<blocks, threads>>>(d, iters, 0.999f, 1e-3f);
+        cudaEventRecord(e1);
+        e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (e != cudaSuccess) return e;
+    const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+    *tflops = (float)(flops / (best * 1e-3) / 1e12);
+    return cudaGetLastError();
+}
+
+cudaError_t fp32_peak(int device, float *unfused_tflops, float *ffma_tflops) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return e;
+    int sm = 0;
+    e = cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    e = time_chain<false>(sm, unfused_tflops);
+    if (e != cudaSuccess) return e;
+    return time_chain<true>(sm, ffma_tflops);
+}
+
+}  // namespace rr

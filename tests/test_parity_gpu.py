@@ -1,0 +1,360 @@
+"""GPU parity tests: the CUDA path (called through the C ABI) against the CPU oracle.
+
+Bar (BASELINE.json north_star): <= 1 LSB per 8-bit channel on >= 99.9 % of pixels. What is actually
+demanded here is stricter wherever the arithmetic allows it:
+  * pixels whose colour involves no libm transcendental (no bgcolor, no LL uv map, no glow powf)
+    must be BIT-EXACT in f32 — +,-,*,/,sqrt,floor are IEEE in both implementations;
+  * pixels that go through atan2f/asinf/powf (CUDA's differ from glibc's by <= 2-4 ulp) must be
+    within 1 LSB after quantisation, and >= 99.9 % of them exact.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+NCPU = os.cpu_count() or 1
+TAG_BG, TAG_REFLECT, TAG_REFRACT = 1, 2, 4
+
+
+def diff_stats(dev, ref):
+    d = np.abs(dev.astype(np.int32) - ref.astype(np.int32)).max(axis=2)
+    return float((d == 0).mean()), float((d <= 1).mean()), int(d.max()), d
+
+
+def device_render(rr, ren, params=None, f32=False):
+    scene = rr.DeviceScene(ren, 0)
+    try:
+        p = params or ren.frame_params()
+        return scene.render_f32(p) if f32 else scene.render_rgb8(p)
+    finally:
+        scene.close()
+
+
+def check_frame(rr, oracle, ren, min_exact=0.999, transcendental_free_tagmask=TAG_BG, allow_le1=1.0):
+    """Render on both sides; u8 within tolerance, f32 bit-exact where no libm call is involved."""
+    ref = oracle.render(ren, threads=NCPU, want_f32=True, want_tags=True)
+    dev8 = device_render(rr, ren)
+    devf = device_render(rr, ren, f32=True)
+    exact, le1, mx, d = diff_stats(dev8, ref["u8"])
+    assert le1 >= allow_le1, f"le1={le1} max={mx}"
+    assert exact >= min_exact, f"exact={exact}"
+    clean = (ref["tags"] & transcendental_free_tagmask) == 0
+    a = devf.view(np.uint32)[clean]
+    b = ref["f32"].view(np.uint32)[clean]
+    nbad = int((a != b).any(axis=-1).sum())
+    assert nbad == 0, f"{nbad} of {int(clean.sum())} transcendental-free pixels differ in f32 bits"
+    # every u8 mismatch sits on a pixel that evaluated bgcolor
+    assert ((d > 0) & clean).sum() == 0
+    return exact, le1
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs at sizes the oracle finishes in seconds
+# ---------------------------------------------------------------------------------------------
+def test_config1_default_640x480_trace(rr, oracle):
+    exact, le1 = check_frame(rr, oracle, rr.default_scene(640, 480), min_exact=0.9995)
+    print(f"config1 exact={exact:.6f} le1={le1:.6f}")
+
+
+def test_default_march_glow(rr, oracle):
+    ren = rr.default_scene(320, 240, use_raymarching=True, glow_effect=1.0)
+    ref = oracle.render(ren, threads=NCPU, want_f32=True, want_tags=True)
+    dev8 = device_render(rr, ren)
+    exact, le1, mx, _ = diff_stats(dev8, ref["u8"])
+    assert le1 >= 0.9995 and exact >= 0.999, (exact, le1, mx)
+
+
+def test_default_march_noglow_bit_exact(rr, oracle):
+    check_frame(rr, oracle, rr.default_scene(320, 240, use_raymarching=True))
+
+
+def test_synthetic_spheres_trace(rr, oracle):
+    ren = rr.synthetic_scene(320, 180, n_spheres=256)
+    check_frame(rr, oracle, ren, min_exact=0.999)
+
+
+def test_synthetic_1024_trace_small(rr, oracle):
+    ren = rr.synthetic_scene(240, 136)
+    check_frame(rr, oracle, ren, min_exact=0.999)
+
+
+def test_synthetic_march(rr, oracle):
+    ren = rr.synthetic_scene(96, 54, n_spheres=64, use_raymarching=True, glow_effect=0.5)
+    ref = oracle.render(ren, threads=NCPU)
+    exact, le1, mx, _ = diff_stats(device_render(rr, ren), ref["u8"])
+    assert le1 >= 0.999 and exact >= 0.995, (exact, le1, mx)
+
+
+# ---------------------------------------------------------------------------------------------
+# ray counters: the device's instrumented kernel must count exactly what the oracle counts
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("march", [False, True])
+def test_ray_counts_match_oracle(rr, oracle, march):
+    ren = rr.default_scene(320, 240, use_raymarching=march, glow_effect=1.0 if march else None)
+    ref = oracle.render(ren, threads=NCPU, want_counts=True)
+    scene = rr.DeviceScene(ren, 0)
+    img, cnt = scene.render_count(ren.frame_params())
+    plain = scene.render_rgb8(ren.frame_params())
+    scene.close()
+    assert cnt.as_dict() == ref["counts"].as_dict()
+    assert np.array_equal(img, plain)  # the instrumented kernel renders the same bytes
+
+
+def test_ray_counts_synthetic(rr, oracle):
+    ren = rr.synthetic_scene(160, 90, n_spheres=128)
+    ref = oracle.render(ren, threads=NCPU, want_counts=True)
+    scene = rr.DeviceScene(ren, 0)
+    _, cnt = scene.render_count(ren.frame_params(), want_image=False)
+    scene.close()
+    assert cnt.as_dict() == ref["counts"].as_dict()
+
+
+# ---------------------------------------------------------------------------------------------
+# materials, uv maps, textures, several floors
+# ---------------------------------------------------------------------------------------------
+def _texture(seed, w, h):
+    return np.random.default_rng(seed).integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+
+
+def _material_zoo_scene(rr, w, h, march=False):
+    RC = rr.RenderColor
+    floor = rr.RenderMaterial.new("floor", RC(1, 1, 0), RC(0, 0, 0), 0, 0.0, 0.0).pattern("Checkerboard").pattern_scale(120.0)
+    wall = rr.RenderMaterial.new("wall", RC(0.2, 0.5, 0.9), RC(0.3, 0.3, 0.3), 8, 0.0, 0.0).pattern(
+        "RepeatedGradation").pattern_scale(77.0)
+    near = rr.RenderMaterial.new("near", RC(0, 0, 0), RC(0, 0, 0), 0, 0.0, 0.0).texture_data(_texture(1, 13, 7), "Nearest")
+    near.pattern_scale(50.0)
+    bil = rr.RenderMaterial.new("bil", RC(0, 0, 0), RC(0.1, 0.1, 0.1), 16, 0.0, 0.0).texture_data(_texture(2, 16, 16),
+                                                                                              "Bilinear")
+    bil.pattern_scale(33.0)
+    ll = rr.RenderMaterial.new("ll", RC(0.9, 0.9, 0.9), RC(0, 0, 0), 24, 0.0, 0.0).pattern("Checkerboard").pattern_angle_scale(0.2)
+    glass = rr.RenderMaterial.new("glass", RC(0.1, 0.1, 0.1), RC(0.4, 0.4, 0.4), 12, 0.7, 1.4)
+    mirror = rr.RenderMaterial.new("mirror", RC(0.05, 0.05, 0.05), RC(0.9, 0.9, 0.9), 24, 0.0, 0.0)
+    glow = rr.RenderMaterial.new("glow", RC(0.8, 0.2, 0.1), RC(0, 0, 0), 24, 0.0, 0.0).glow_dist(3.0)
+    objs = [
+        rr.RenderFloor.new_raw(floor, (0, -300, 0), (0, 1, 0)).uvmap("ZX"),
+        rr.RenderFloor.new_raw(wall, (0, 0, 900), (0.0, 0.0, -2.0)).uvmap("XY"),      # un-normalised normal (Q22)
+        rr.RenderSphere.new(near, 90, (-260, -120, 300)).uvmap("YZ"),
+        rr.RenderSphere.new(bil, 80, (-60, -200, 260)).uvmap("XY"),
+        rr.RenderSphere.new(ll, 85, (150, -100, 330)).uvmap("LL"),
+        rr.RenderSphere.new(glass, 70, (40, -210, 60)),
+        rr.RenderSphere.new(mirror, 100, (330, -30, 420)),
+        rr.RenderSphere.new(glow, 40, (-150, -30, 120)),
+        rr.RenderSphere.new(glass, 60, (150, -230, 120)),
+    ]
+    f32 = np.float32
+    return (rr.RenderEnv.new((0, -150, -300), (f32(0.05), -rr.scene.PI / f32(2) + f32(0.1), -rr.scene.PI / f32(2)), w, h, 1.0,
+                             f32(h) / f32(w))
+            .objects(objs).light((50, 60, -50)).use_raymarching(march).glow_effect(0.8 if march else None))
+
+
+def test_material_zoo_trace(rr, oracle):
+    ren = _material_zoo_scene(rr, 400, 300)
+    ref = oracle.render(ren, threads=NCPU, want_f32=True, want_tags=True)
+    dev8 = device_render(rr, ren)
+    exact, le1, mx, d = diff_stats(dev8, ref["u8"])
+    assert le1 >= 0.9995 and exact >= 0.998, (exact, le1, mx)
+
+
+def test_material_zoo_march(rr, oracle):
+    ren = _material_zoo_scene(rr, 160, 120, march=True)
+    ref = oracle.render(ren, threads=NCPU)
+    exact, le1, mx, _ = diff_stats(device_render(rr, ren), ref["u8"])
+    assert le1 >= 0.999 and exact >= 0.995, (exact, le1, mx)
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,h", [(1, 1), (7, 3), (37, 23), (64, 1), (9, 64)])
+def test_ragged_sizes(rr, oracle, w, h):
+    ren = rr.default_scene(w, h)
+    ref = oracle.render(ren)["u8"]
+    dev = device_render(rr, ren)
+    assert dev.shape == ref.shape
+    _, le1, _, _ = diff_stats(dev, ref)
+    assert le1 == 1.0
+
+
+def test_empty_frame_and_empty_scene(rr, oracle):
+    ren = rr.default_scene(0, 0)
+    assert device_render(rr, ren).shape == (0, 0, 3)
+    sky = rr.default_scene(64, 48).objects([])
+    ref = oracle.render(sky)["u8"]
+    _, le1, _, _ = diff_stats(device_render(rr, sky), ref)
+    assert le1 == 1.0
+
+
+@pytest.mark.parametrize("refl,refr", [(0, 10), (1, 10), (3, 0), (3, 1), (5, 4), (2, 32)])
+def test_depth_limits(rr, oracle, refl, refr):
+    ren = rr.synthetic_scene(160, 90, n_spheres=96)
+    ren.max_reflections, ren.max_refractions = refl, refr
+    check_frame(rr, oracle, ren, min_exact=0.998)
+
+
+def test_unsupported_depth_is_an_error(rr):
+    ren = rr.default_scene(16, 16)
+    ren.max_refractions = 33
+    scene = rr.DeviceScene(ren, 0)
+    with pytest.raises(rr.ffi.RrError) as e:
+        scene.render_rgb8(ren.frame_params())
+    assert e.value.code == rr.ffi.RR_ERR_UNSUPPORTED
+    scene.close()
+
+
+def test_bad_scene_is_rejected(rr):
+    ren = rr.default_scene(16, 16)
+    flat = ren.flatten()
+    flat.desc.objects[1].material = 99
+    h = C.c_void_p()
+    rc = rr.ffi.load().rr_scene_create(C.byref(flat.desc), 0, C.byref(h))
+    assert rc == rr.ffi.RR_ERR_BAD_ARG and not h.value
+    flat = ren.flatten()
+    flat.desc.objects[0].uvmap = 4  # the oracle's test-only legacy mapping must not be accepted
+    assert rr.ffi.load().rr_scene_create(C.byref(flat.desc), 0, C.byref(h)) == rr.ffi.RR_ERR_BAD_ARG
+
+
+def test_row_stride_padding(rr):
+    ren = rr.default_scene(40, 24)
+    scene = rr.DeviceScene(ren, 0)
+    p = ren.frame_params()
+    packed = scene.render_rgb8(p)
+    stride = 40 * 3 + 8
+    buf = np.full((24, stride), 0xAB, dtype=np.uint8)
+    rr.ffi.check(scene.lib.rr_render_rgb8(scene.handle, C.byref(p), buf.ctypes.data_as(C.c_void_p), stride))
+    scene.close()
+    assert np.array_equal(buf[:, :120].reshape(24, 40, 3), packed)
+    assert (buf[:, 120:] == 0xAB).all()
+
+
+def test_pointproc_render_signature(rr, oracle):
+    """render(ren, pointproc, thread_count): pointproc sees every pixel exactly once, row-major."""
+    ren = rr.default_scene(24, 16)
+    seen = {}
+    rr.render(ren, lambda x, y, c: seen.__setitem__((x, y), (c.r, c.g, c.b)), 8)
+    assert len(seen) == 24 * 16
+    ref = oracle.render(ren, want_f32=True, want_tags=True)
+    for (x, y), c in seen.items():
+        if ref["tags"][y, x] & TAG_BG == 0:
+            assert tuple(np.float32(v) for v in c) == tuple(ref["f32"][y, x])
+
+
+def test_concurrent_calls_on_one_handle(rr):
+    """webserver.rs:268-280: several host threads may be inside render() at once."""
+    ren = rr.default_scene(200, 120)
+    scene = rr.DeviceScene(ren, 0)
+    base = scene.render_rgb8(ren.frame_params())
+    outs, errs = [None] * 6, []
+
+    def work(i):
+        try:
+            outs[i] = scene.render_rgb8(ren.frame_params())
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    scene.close()
+    assert not errs
+    assert all(np.array_equal(o, base) for o in outs)
+
+
+# ---------------------------------------------------------------------------------------------
+# row bands (multi-GPU sharding) — N-shard image must be byte-identical to the 1-shard image
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,band", [(2, 16), (3, 8), (8, 32), (4, 5)])
+def test_row_bands_reassemble(rr, n, band):
+    import torch
+
+    ren = rr.default_scene(256, 150)
+    scene = rr.DeviceScene(ren, 0)
+    full = scene.render_rgb8(ren.frame_params())
+    shard_rows = [rr.frame_rows(ren.frame_params(band, k, n)) for k in range(n)]
+    stride = max(shard_rows) * 256 * 3
+    packed = torch.zeros(n * stride, dtype=torch.uint8, device="cuda:0")
+    for k in range(n):
+        p = ren.frame_params(band, k, n)
+        scene.render_rgb8_device(p, packed.data_ptr() + k * stride)
+        host = scene.render_rgb8(p)
+        ys = [y for y in range(150) if (y // band) % n == k]
+        assert np.array_equal(host, full[ys])
+    frame = torch.zeros(150 * 256 * 3, dtype=torch.uint8, device="cuda:0")
+    p0 = ren.frame_params(band, 0, n)
+    rr.ffi.check(scene.lib.rr_bands_unpack_device(C.byref(p0), C.c_void_p(packed.data_ptr()), stride,
+                                                  C.c_void_p(frame.data_ptr()), None))
+    torch.cuda.synchronize()
+    scene.close()
+    assert np.array_equal(frame.cpu().numpy().reshape(150, 256, 3), full)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: oracle where it finishes in seconds, size-independent properties otherwise
+# ---------------------------------------------------------------------------------------------
+def test_config2_default_4k_trace_vs_oracle(rr, oracle):
+    ren = rr.default_scene(3840, 2160)
+    ref = oracle.render(ren, threads=NCPU, want_counts=True)
+    scene = rr.DeviceScene(ren, 0)
+    dev = scene.render_rgb8(ren.frame_params())
+    _, cnt = scene.render_count(ren.frame_params(), want_image=False)
+    scene.close()
+    exact, le1, mx, _ = diff_stats(dev, ref["u8"])
+    print(f"config2 4K: exact={exact:.6f} le1={le1:.6f} max={mx} rays={cnt.rays()}")
+    assert le1 == 1.0 and exact >= 0.9995
+    assert cnt.as_dict() == ref["counts"].as_dict()
+    assert cnt.rays() == 15626224
+
+
+def test_config3_march_glow_4k_properties(rr, oracle):
+    """4K march+glow: oracle comparison on a 1/4-scale crop of rows, shard-invariance on the full frame."""
+    ren = rr.default_scene(3840, 2160, use_raymarching=True, glow_effect=1.0)
+    scene = rr.DeviceScene(ren, 0)
+    full = scene.render_rgb8(ren.frame_params())
+    # one interleaved shard out of 16 (135 rows) is checked against the oracle at full resolution
+    p = ren.frame_params(band_rows=1, band_index=7, band_count=16)
+    dev = scene.render_rgb8(p)
+    scene.close()
+    assert np.array_equal(dev, full[7::16])
+    ref = oracle.render(ren, params=p, threads=NCPU)["u8"]
+    exact, le1, mx, _ = diff_stats(dev, ref)
+    print(f"config3 4K march rows 7::16: exact={exact:.6f} le1={le1:.6f} max={mx}")
+    assert le1 >= 0.9995 and exact >= 0.999
+
+
+def test_config4_synthetic_1024_4k_properties(rr, oracle):
+    ren = rr.synthetic_scene(3840, 2160)
+    text = ren.serialize()                 # -s ... -d round trip (BASELINE config 4)
+    ren2 = rr.default_scene(3840, 2160)
+    ren2.deserialize(text)
+    scene = rr.DeviceScene(ren2, 0)
+    full = scene.render_rgb8(ren2.frame_params())
+    p = ren2.frame_params(band_rows=1, band_index=3, band_count=32)
+    dev = scene.render_rgb8(p)
+    scene.close()
+    assert np.array_equal(dev, full[3::32])
+    ref = oracle.render(ren, params=ren.frame_params(1, 3, 32), threads=NCPU)["u8"]
+    exact, le1, mx, _ = diff_stats(dev, ref)
+    print(f"config4 4K synthetic rows 3::32: exact={exact:.6f} le1={le1:.6f} max={mx}")
+    assert le1 >= 0.9995 and exact >= 0.999
+
+
+def test_config5_8k_bands_identical_to_single(rr, oracle):
+    ren = rr.default_scene(7680, 4320)
+    scene = rr.DeviceScene(ren, 0)
+    full = scene.render_rgb8(ren.frame_params())
+    for n in (2, 4, 8):
+        out = np.empty_like(full)
+        for k in range(n):
+            p = ren.frame_params(16, k, n)
+            rows = scene.render_rgb8(p)
+            ys = np.array([y for y in range(4320) if (y // 16) % n == k])
+            out[ys] = rows
+        assert np.array_equal(out, full), f"{n}-shard frame differs from the 1-shard frame"
+    scene.close()
+    ref = oracle.render(ren, threads=NCPU)["u8"]
+    exact, le1, mx, _ = diff_stats(full, ref)
+    print(f"config5 8K: exact={exact:.6f} le1={le1:.6f} max={mx}")
+    assert le1 == 1.0 and exact >= 0.9995

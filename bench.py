@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the per-pixel tracing path (BASELINE.json metric: Mrays/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+  N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+A "step" renders one whole frame of the workload:
+  N=1  "default-4k-trace"  = BASELINE.json configs[1]: built-in scene, 3840x2160, ray-trace mode.
+  N>1  "default-8k-trace-bands" = configs[4]: built-in scene, 7680x4320, interleaved 16-row bands
+       over the N ranks, bands gathered to rank 0 over NCCL and un-interleaved there.
+`value` = reference-equivalent rays (one ray = one scene-level raycast(); counted by
+the instrumented kernel and checked against the oracle in tests/) per second of device time with the
+scene resident in HBM; `e2e` = same through rr_render_rgb8 into pinned HOST memory (wall clock,
+includes the D2H of the frame). The reference arm (--impl reference) times the CPU oracle
+(oracle/, the C++ restatement of the reference: no Rust toolchain exists here) on all host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (width, height, march, glow, scene)
+    "default-4k-trace": (3840, 2160, False, None, "default"),
+    "default-8k-trace-bands": (7680, 4320, False, None, "default"),
+    "default-8k-trace": (7680, 4320, False, None, "default"),
+    "default-4k-march-glow": (3840, 2160, True, 1.0, "default"),
+    "synthetic1024-4k-trace": (3840, 2160, False, None, "synthetic"),
+    "default-640x480-trace": (640, 480, False, None, "default"),
+}
+BAND_ROWS = 16
+
+# ALGORITHMIC flops per unit of work (1 flop = one f32 add/sub/mul/div/sqrt/min/max/neg)
+FLOPS = dict(pixel_setup=71, sphere_test=19, floor_test=15, hit_point=6, sphere_normal=12, shading=54,
+             refract=38, bounce=28, bg=27 + 6, quantise=9, sphere_dist=12, floor_dist=10, march_step=7, glow=5)
+
+
+def algorithmic_flops(c, march):
+    """flops(frame) = sum(counter x constant) with the counters of the reference's brute-force algorithm."""
+    floor_tests = c["object_tests"] - c["sphere_tests"]
+    hits = c["shadow"]  # one shading() call per hit, one shadow ray per shading() call
+    f = FLOPS
+    total = c["pixels"] * (f["pixel_setup"] + f["quantise"])
+    if march:
+        total += c["sphere_tests"] * f["sphere_dist"] + floor_tests * f["floor_dist"] + c["march_steps"] * f["march_step"]
+        total += (c["primary"] + c["refract"]) * f["glow"]
+    else:
+        total += c["sphere_tests"] * f["sphere_test"] + floor_tests * f["floor_test"]
+    total += hits * (f["hit_point"] + f["shading"] + f["bounce"]) + c["sphere_hits"] * f["sphere_normal"]
+    total += c["refract"] * f["refract"] + c["bg_evals"] * f["bg"]
+    return int(total)
+
+
+def make_env(rr, name):
+    w, h, march, glow, kind = WORKLOADS[name]
+    if kind == "synthetic":
+        return rr.synthetic_scene(w, h, use_raymarching=march, glow_effect=glow)
+    return rr.default_scene(w, h, use_raymarching=march, glow_effect=glow)
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_arm(ob, ren, threads, reps, params=None):
+    """Time the oracle (CPU restatement of the reference path) on `threads` host threads."""
+    best = None
+    for _ in range(reps):
+        t = time.perf_counter()
+        ob.render(ren, params=params, threads=threads, want_u8=True)
+        dt = time.perf_counter() - t
+        best = dt if best is None or dt < best else best
+    return best
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores, same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import ray_rust_b200 as rr
+    from oracle import binding as ob
+
+    name = args.workload or ("default-4k-trace" if args.gpus == 1 else "default-8k-trace-bands")
+    ren = make_env(rr, name)
+    threads = os.cpu_count() or 1
+    counts = ob.render(ren, threads=threads, want_u8=False, want_counts=True)["counts"]
+    rays = counts.rays()
+    for _ in range(args.warmup):
+        ob.render(ren, threads=threads)
+    times = []
+    for _ in range(args.steps):
+        t = time.perf_counter()
+        ob.render(ren, threads=threads)
+        times.append(time.perf_counter() - t)
+    ms = 1e3 * sum(times) / len(times)
+    v = rays / (ms * 1e-3) / 1e6
+    w, h = WORKLOADS[name][:2]
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "width": w, "height": h, "rays_per_frame": rays,
+                   "note": "CPU oracle (C++ restatement of the reference's render(); the Rust binary cannot be built here), "
+                           "render only, -t = host cores"},
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} full {w}x{h} frames, mean"},
+        "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = args.steps or 10
+        args.warmup = 1 if args.warmup is None else args.warmup
+        return run_reference(args)
+    args.steps = args.steps or 50
+    args.warmup = 5 if args.warmup is None else max(3, args.warmup)
+
+    import numpy as np
+    import torch
+
+    import ray_rust_b200 as rr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = rr.ffi.load()
+
+    name = args.workload or ("default-4k-trace" if world == 1 else "default-8k-trace-bands")
+    W, H, march, glow, _ = WORKLOADS[name]
+    ren = make_env(rr, name)
+    scene = rr.DeviceScene(ren, local_rank)
+    sharded = world > 1
+    p = ren.frame_params(BAND_ROWS, rank, world) if sharded else ren.frame_params()
+    my_rows = rr.frame_rows(p)
+    max_rows = max(rr.frame_rows(ren.frame_params(BAND_ROWS, r, world)) for r in range(world)) if sharded else H
+    shard_bytes = max_rows * W * 3
+
+    # ---- ray counts of the whole frame (reference-equivalent; instrumented kernel, untimed) ----
+    _, cnt = scene.render_count(ren.frame_params(), want_image=False)
+    counts = cnt.as_dict()
+    rays = cnt.rays()
+    flops = algorithmic_flops(counts, march)
+
+    stream = torch.cuda.current_stream(dev)
+    out = torch.empty(shard_bytes, dtype=torch.uint8, device=dev)
+    gathered = torch.empty(world * shard_bytes, dtype=torch.uint8, device=dev) if (sharded and rank == 0) else None
+    frame = torch.empty(H * W * 3, dtype=torch.uint8, device=dev) if (sharded and rank == 0) else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    launches = 0
+
+    def step():
+        n = 1
+        scene.render_rgb8_device(p, out.data_ptr(), stream=stream.cuda_stream)
+        if sharded:
+            glist = list(gathered.chunk(world)) if rank == 0 else None
+            dist.gather(out, glist, dst=0)
+            if rank == 0:
+                rr.ffi.check(lib.rr_bands_unpack_device(C.byref(p), C.c_void_p(gathered.data_ptr()), shard_bytes,
+                                                        C.c_void_p(frame.data_ptr()), C.c_void_p(stream.cuda_stream)))
+                n += 1
+        return n
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)  # evict the previous frame from L2 (not timed)
+        if dist is not None:
+            dist.barrier()
+        ev[i][0].record(stream)
+        kev[i][0].record(stream)
+        scene.render_rgb8_device(p, out.data_ptr(), stream=stream.cuda_stream)
+        kev[i][1].record(stream)
+        n = 1
+        if sharded:
+            glist = list(gathered.chunk(world)) if rank == 0 else None
+            dist.gather(out, glist, dst=0)
+            if rank == 0:
+                rr.ffi.check(lib.rr_bands_unpack_device(C.byref(p), C.c_void_p(gathered.data_ptr()), shard_bytes,
+                                                        C.c_void_p(frame.data_ptr()), C.c_void_p(stream.cuda_stream)))
+                n += 1
+        ev[i][1].record(stream)
+        launches += n
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    kern_ms = [a.elapsed_time(b) for a, b in kev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    kmean = torch.tensor([sum(kern_ms) / len(kern_ms)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kmean, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / args.steps
+    value = rays / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: the reference-facing call, frame delivered to pinned HOST memory -----------------
+    host = C.c_void_p()
+    rr.ffi.check(lib.rr_host_alloc(max(1, my_rows * W * 3), C.byref(host)))
+    for _ in range(3):
+        rr.ffi.check(lib.rr_render_rgb8(scene.handle, C.byref(p), host, 0))
+    barrier()
+    e2e_steps = max(5, min(args.steps, 50))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rr.ffi.check(lib.rr_render_rgb8(scene.handle, C.byref(p), host, 0))
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_s.item()) * 1e3 / e2e_steps
+    e2e_value = rays / (e2e_ms * 1e-3) / 1e6
+    lib.rr_host_free(host)
+
+    if rank != 0:
+        scene.close()
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (the render kernel) -----------------------------------
+    a, b = C.c_float(), C.c_float()
+    rr.ffi.check(lib.rr_fp32_peak_tflops(local_rank, C.byref(a), C.byref(b)))
+    peaks = measured_peaks()
+    sm_max = (peaks or {}).get("sm_max_mhz", 1965.0)
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    derived_unfused = 128 * n_sm * sm_max * 1e6 / 1e12  # 1 flop/lane/clk: FMUL and FADD issue separately (-fmad=false)
+    kernel_ms = float(kmean.item())
+    # one launch renders this rank's share of the frame
+    share = (my_rows / H) if sharded else 1.0
+    achieved = flops * share / (kernel_ms * 1e-3) / 1e12
+    fb_bytes = my_rows * W * 3
+    hbm_peak = (peaks or {}).get("hbm_gbs", 6650.0)
+    roofline = {
+        "bound": "fp32", "achieved": achieved, "peak": derived_unfused, "unit": "TFLOP/s", "frac": achieved / derived_unfused,
+        "traffic": None,
+        "kernel": "rr::march_kernel" if march else "rr::trace_kernel", "kernel_ms": kernel_ms,
+        "algorithmic_flops_per_launch": int(flops * share),
+        "peak_source": f"derived: 128 FP32 lanes x {n_sm} SMs x {sm_max:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz"
+                       f"{'' if peaks else ' absent: fallback 1965'}) x 1 flop (unfused FMUL/FADD, -fmad=false for bit parity); "
+                       "neither MEASURED_PEAKS.json nor the profiling guide carries an FP32 non-tensor figure",
+        "measured_unfused_tflops": a.value, "measured_ffma_tflops": b.value,
+        "frac_of_measured_unfused": achieved / a.value if a.value else None,
+        "hbm": {"algorithmic_bytes_per_launch": fb_bytes, "achieved_gbs": fb_bytes / (kernel_ms * 1e-3) / 1e9,
+                "peak_gbs": hbm_peak, "frac": fb_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
+    }
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        roofline["traffic"] = prof.get(name, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---- CPU baseline beside it (oracle port on all host cores; bounded sample) -----------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import binding as ob
+
+        threads = os.cpu_count() or 1
+        reps = 3 if not march else 1
+        if march or WORKLOADS[name][4] == "synthetic":
+            # bounded sample: one interleaved 1/16 of the rows, scaled
+            sp = ren.frame_params(1, 5, 16)
+            sub = ob.render(ren, params=sp, threads=threads, want_u8=False, want_counts=True)["counts"].rays()
+            best = cpu_arm(ob, ren, threads, reps, params=sp)
+            cpu = {"value": sub / best / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                   "sample": f"rows 5::16 of the {W}x{H} frame ({sub} rays), best of {reps}"}
+        else:
+            best = cpu_arm(ob, ren, threads, reps)
+            cpu = {"value": rays / best / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                   "sample": f"full {W}x{H} frame ({rays} rays), best of {reps}", "frame_ms": best * 1e3}
+
+    line = {
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "width": W, "height": H, "mode": "raymarch" if march else "raytrace",
+                   "max_reflections": 3, "max_refractions": 10, "rays_per_frame": rays, "ray_classes": counts,
+                   "l2": "flushed between timed steps (256 MiB write, untimed)",
+                   "parallelism": f"row-bands{world}x{BAND_ROWS}+nccl-gather" if sharded else "1gpu",
+                   "scene_resident": True},
+        "frame_ms": ms_per_step,
+        "kernel_ms": kernel_ms,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_frame": e2e_ms, "h2d_bytes_per_step": C.sizeof(rr.ffi.rr_frame_params),
+                "d2h_bytes_per_step": my_rows * W * 3, "api": "rr_render_rgb8 (C ABI) -> pinned host RGB8 frame",
+                "note": "per-rank bands to each rank's host buffer" if sharded else "whole frame"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "wall_s_timed_region": wall_s,
+    }
+    print(json.dumps(line), flush=True)
+    scene.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

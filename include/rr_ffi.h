@@ -136,6 +136,8 @@ typedef struct rr_ray_counts {
     uint64_t object_tests;      /* trace: per-object raycast calls; march: per-object distance calls */
     uint64_t march_steps;       /* march mode: iterations of raymarch_single's loop */
     uint64_t bg_evals;          /* bgproc invocations (reference-equivalent count) */
+    uint64_t sphere_tests;      /* the part of object_tests that went to spheres */
+    uint64_t sphere_hits;       /* shading() calls whose object is a sphere (normal = 3 div + sqrt) */
 } rr_ray_counts;
 
 typedef struct rr_scene rr_scene; /* opaque: device-resident flattened scene + per-handle stream */

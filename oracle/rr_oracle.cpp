@@ -388,7 +388,7 @@ inline float raycast(const Env &ren, const Vec3 &vi, const Vec3 &eye, int64_t ig
     for (size_t idx = 0; idx < n; ++idx) {
         if (ig >= 0 && (size_t)ig == idx) continue;
         const rr_object &o = ren.obj(idx);
-        if (COUNT) ins->c.object_tests++;
+        if (COUNT) { ins->c.object_tests++; if (o.kind == RR_SPHERE) ins->c.sphere_tests++; }
         float obj_t = (o.kind == RR_SPHERE) ? sphere_raycast<COUNT>(o, vi, eye, t, flags, ins)
                                             : floor_raycast(o, vi, eye, t);
         if (obj_t < t) {
@@ -411,7 +411,7 @@ inline void distance_estimate(const Env &ren, const Vec3 &vi, int64_t ig, float 
     for (size_t idx = 0; idx < n; ++idx) {
         if (ig >= 0 && (size_t)ig == idx) continue;
         const rr_object &o = ren.obj(idx);
-        if (COUNT) ins->c.object_tests++;
+        if (COUNT) { ins->c.object_tests++; if (o.kind == RR_SPHERE) ins->c.sphere_tests++; }
         float dist = (o.kind == RR_SPHERE) ? sphere_distance(o, vi) : floor_distance(o, vi);
         if (dist < closest_dist) {
             closest_dist = dist;
@@ -491,7 +491,7 @@ Color shading(const Env &ren, size_t idx, const Vec3 &n, const Vec3 &pt, const V
         const Vec3 ray = ren.light;
         k1 = 0.2f;
         bool lit;
-        if (COUNT) ins->c.shadow++;
+        if (COUNT) { ins->c.shadow++; if (ren.obj(idx).kind == RR_SPHERE) ins->c.sphere_hits++; }
         if (ren.use_raymarching) {
             MarchResult r = raymarch_single<COUNT>(ren, reflected_ray, ray, (int64_t)idx, ins);
             lit = FAR_AWAY <= r.travel_dist || MAX_ITER <= r.iter || 0.0f < ren.mat_of(idx).t;
@@ -716,6 +716,7 @@ void render_rows(const Env &ren, const std::vector<int32_t> &rows, int threads, 
         counts->pixels += ins.c.pixels; counts->primary += ins.c.primary; counts->reflect += ins.c.reflect;
         counts->refract += ins.c.refract; counts->shadow += ins.c.shadow; counts->object_tests += ins.c.object_tests;
         counts->march_steps += ins.c.march_steps; counts->bg_evals += ins.c.bg_evals;
+        counts->sphere_tests += ins.c.sphere_tests; counts->sphere_hits += ins.c.sphere_hits;
     };
     if (threads <= 1) {  // render.rs:829-835
         Instr ins;

@@ -327,6 +327,10 @@ int rr_render_rgb8(rr_scene *s, const rr_frame_params *params, uint8_t *out, siz
     int nchunk = (int)((packed * rows) / (4u << 20));  // ~4 MiB per chunk, at most 8 chunks
     if (nchunk < 1) nchunk = 1;
     if (nchunk > 8) nchunk = 8;
+    // Chunking pays only while the kernel is shorter than the copy. Long kernels (ray marching with
+    // its heavy-tailed rows, scenes with many objects) lose more to per-chunk tails than the
+    // overlap wins: render those in one launch.
+    if (P.use_raymarching || s->G.n_objects > 64) nchunk = 1;
     int chunk_rows = (rows + nchunk - 1) / nchunk;
     chunk_rows = (chunk_rows + 3) & ~3;  // whole 4-row tiles
     CU(cudaEventRecord(s->ev0, s->stream));
@@ -392,7 +396,7 @@ int rr_render_count(rr_scene *s, const rr_frame_params *params, uint8_t *out, si
     CU(cudaStreamSynchronize(s->stream));
     counts->pixels = h.pixels; counts->primary = h.primary; counts->reflect = h.reflect; counts->refract = h.refract;
     counts->shadow = h.shadow; counts->object_tests = h.object_tests; counts->march_steps = h.march_steps;
-    counts->bg_evals = h.bg_evals;
+    counts->bg_evals = h.bg_evals; counts->sphere_tests = h.sphere_tests; counts->sphere_hits = h.sphere_hits;
     return RR_OK;
 }
 

@@ -40,17 +40,6 @@ __device__ __forceinline__ MarchView stage_march(const DevScene &G, float4 *smem
     return S;
 }
 
-__device__ __forceinline__ void flush_counters_m(const Counters &c, Counters *g) {
-    unsigned long long v[8] = {c.pixels, c.primary, c.reflect, c.refract, c.shadow, c.object_tests, c.march_steps, c.bg_evals};
-    unsigned long long *gp = reinterpret_cast<unsigned long long *>(g);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        unsigned long long x = v[k];
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        if ((threadIdx.x & 31) == 0 && x) atomicAdd(&gp[k], x);
-    }
-}
-
 template <bool COUNT, bool F32OUT, bool STAGE, bool GLOW>
 __global__ void __launch_bounds__(MARCH_THREADS)
 march_kernel(const DevScene G, const FrameParams P, void *__restrict__ out, size_t row_stride, Counters *gcnt,
@@ -86,7 +75,7 @@ march_kernel(const DevScene G, const FrameParams P, void *__restrict__ out, size
             store_tile_rgb8(reinterpret_cast<uint8_t *>(out), row_stride, x0, ly0, W, rows, rgb, fast_store != 0);
         }
     }
-    if (COUNT) flush_counters_m(cnt, gcnt);
+    if (COUNT) flush_counters(cnt, gcnt);
 }
 
 static size_t march_smem_bytes(const DevScene &G) {

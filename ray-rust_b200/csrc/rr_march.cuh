@@ -135,6 +135,7 @@ __device__ __forceinline__ V3 march_pixel(const DevScene &G, const MarchView &S,
             else cnt.reflect++;
             cnt.march_steps += (unsigned long long)r.iter;
             cnt.object_tests += (unsigned long long)r.iter * (unsigned long long)(G.n_objects - (ig >= 0 ? 1 : 0));
+            cnt.sphere_tests += (unsigned long long)r.iter * (unsigned long long)spheres_tested(G, ig);
         }
         if (r.min_dist < mmd) mmd = r.min_dist;
         bool frame_done;
@@ -170,6 +171,8 @@ __device__ __forceinline__ V3 march_pixel(const DevScene &G, const MarchView &S,
                     cnt.shadow++;
                     cnt.march_steps += (unsigned long long)sh.iter;
                     cnt.object_tests += (unsigned long long)sh.iter * (unsigned long long)(G.n_objects - 1);
+                    cnt.sphere_tests += (unsigned long long)sh.iter * (unsigned long long)spheres_tested(G, idx);
+                    if (ob.x == 0) cnt.sphere_hits++;
                 }
                 const bool lit = FAR_AWAY <= sh.travel_dist || MAX_ITER <= sh.iter || 0.0f < m.t;
                 if (lit) {
@@ -249,6 +252,7 @@ __device__ __forceinline__ V3 march_pixel(const DevScene &G, const MarchView &S,
                     cnt.reflect++;
                     cnt.march_steps += (unsigned long long)r.iter;
                     cnt.object_tests += (unsigned long long)r.iter * (unsigned long long)(G.n_objects - (ig >= 0 ? 1 : 0));
+                    cnt.sphere_tests += (unsigned long long)r.iter * (unsigned long long)spheres_tested(G, ig);
                 }
             }
             frame_done = true;

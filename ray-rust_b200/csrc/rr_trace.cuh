@@ -127,6 +127,7 @@ __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneView &S,
             else if (ray_class == 1) cnt.refract++;
             else cnt.reflect++;
             cnt.object_tests += (unsigned long long)(G.n_objects - (ig >= 0 ? 1 : 0));
+            cnt.sphere_tests += (unsigned long long)spheres_tested(G, ig);
         }
         const Hit h = raycast(S, vi, eye, ig, flags);
         bool frame_done;
@@ -155,6 +156,8 @@ __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneView &S,
                 if (COUNT) {
                     cnt.shadow++;
                     cnt.object_tests += (unsigned long long)(G.n_objects - 1);
+                    cnt.sphere_tests += (unsigned long long)spheres_tested(G, idx);
+                    if (ob.x == 0) cnt.sphere_hits++;
                 }
                 const Hit sh = raycast(S, shadow_org, light, idx, 0u);
                 bool lit = sh.t >= RR_INF;

@@ -97,6 +97,8 @@ class rr_ray_counts(C.Structure):
         ("object_tests", C.c_uint64),
         ("march_steps", C.c_uint64),
         ("bg_evals", C.c_uint64),
+        ("sphere_tests", C.c_uint64),
+        ("sphere_hits", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -43,6 +43,7 @@ struct rr_scene {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     rr::DevScene G{};
+    rr::SceneHead H{};
     rr::LaunchInfo li{};
     std::vector<void *> allocs;
     std::mutex mu;
@@ -114,7 +115,7 @@ rr::FrameParams to_dev(const rr_frame_params *p) {
 int launch(rr_scene *s, const rr::FrameParams &P, void *d_out, size_t row_stride, bool f32, rr::Counters *d_cnt,
            cudaStream_t st) {
     cudaError_t e = P.use_raymarching ? rr::launch_march(s->G, P, d_out, row_stride, f32, d_cnt, s->d_work, st, s->li)
-                                      : rr::launch_trace(s->G, P, d_out, row_stride, f32, d_cnt, st, s->li);
+                                      : rr::launch_trace(s->G, s->H, P, d_out, row_stride, f32, d_cnt, st, s->li);
     if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
     return RR_OK;
 }
@@ -243,6 +244,11 @@ int rr_scene_create(const rr_scene_desc *desc, int device, rr_scene **out) {
         (rc = upload(s, flo_oi, &G.flo_oi)) || (rc = upload(s, obj_a, &G.obj_a)) || (rc = upload(s, obj_n, &G.obj_n)) ||
         (rc = upload(s, obj_b, &G.obj_b)) || (rc = upload(s, mats, &G.mat)) || (rc = upload(s, tex, &G.tex)))
         return bail(rc);
+
+    for (int k = 0; k < rr::RR_HEAD_SPHERES && k < (int)sph.size(); ++k) { s->H.sph[k] = sph[k]; s->H.sph_oi[k] = sph_oi[k]; }
+    for (int k = 0; k < rr::RR_HEAD_FLOORS && k < (int)flo_o.size(); ++k) {
+        s->H.flo_o[k] = flo_o[k]; s->H.flo_n[k] = flo_n[k]; s->H.flo_oi[k] = flo_oi[k];
+    }
 
     cudaError_t e;
     int sm = 0, optin = 0;

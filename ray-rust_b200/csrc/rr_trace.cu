@@ -3,7 +3,7 @@
 //
 // Mapping: a warp owns an 8x4 pixel tile (coherent primary rays, 24-byte row runs for the RGB8
 // store); warps walk the tile list with a static grid stride from a persistent grid of
-// (SM count x resident blocks), so the scene is staged into shared memory once per block.
+// (SM count x resident blocks), so the scene tail is staged into shared memory once per block.
 // The kernel is FP32-ALU / divergence bound: compiled with -fmad=false for bit parity, no tensor
 // cores, DRAM traffic = the framebuffer store only.
 #include "rr_kernels.h"
@@ -12,38 +12,44 @@
 namespace rr {
 
 constexpr int TRACE_THREADS = 256;
+#ifndef RR_TRACE_MIN_BLOCKS
+#define RR_TRACE_MIN_BLOCKS 4
+#endif
 
+// Only the list tails (objects beyond the SceneHead) are staged; small scenes stage nothing.
 __device__ __forceinline__ SceneView stage_scene(const DevScene &G, float4 *smem, bool stage) {
     SceneView S;
     S.n_spheres = G.n_spheres;
     S.n_floors = G.n_floors;
-    if (!stage) {
-        S.sph = G.sph; S.sph_oi = G.sph_oi; S.flo_o = G.flo_o; S.flo_n = G.flo_n; S.flo_oi = G.flo_oi;
-        return S;
-    }
+    S.sph = G.sph; S.sph_oi = G.sph_oi; S.flo_o = G.flo_o; S.flo_n = G.flo_n; S.flo_oi = G.flo_oi;
+    if (!stage) return S;
+    const int ts = max(G.n_spheres - RR_HEAD_SPHERES, 0), tf = max(G.n_floors - RR_HEAD_FLOORS, 0);
+    if (ts + tf == 0) return S;
     float4 *sph = smem;
-    float4 *flo_o = sph + G.n_spheres;
-    float4 *flo_n = flo_o + G.n_floors;
-    int *sph_oi = reinterpret_cast<int *>(flo_n + G.n_floors);
-    int *flo_oi = sph_oi + G.n_spheres;
-    for (int i = threadIdx.x; i < G.n_spheres; i += blockDim.x) {
-        sph[i] = G.sph[i];
-        sph_oi[i] = G.sph_oi[i];
+    float4 *flo_o = sph + ts;
+    float4 *flo_n = flo_o + tf;
+    int *sph_oi = reinterpret_cast<int *>(flo_n + tf);
+    int *flo_oi = sph_oi + ts;
+    for (int i = threadIdx.x; i < ts; i += blockDim.x) {
+        sph[i] = G.sph[RR_HEAD_SPHERES + i];
+        sph_oi[i] = G.sph_oi[RR_HEAD_SPHERES + i];
     }
-    for (int i = threadIdx.x; i < G.n_floors; i += blockDim.x) {
-        flo_o[i] = G.flo_o[i];
-        flo_n[i] = G.flo_n[i];
-        flo_oi[i] = G.flo_oi[i];
+    for (int i = threadIdx.x; i < tf; i += blockDim.x) {
+        flo_o[i] = G.flo_o[RR_HEAD_FLOORS + i];
+        flo_n[i] = G.flo_n[RR_HEAD_FLOORS + i];
+        flo_oi[i] = G.flo_oi[RR_HEAD_FLOORS + i];
     }
     __syncthreads();
-    S.sph = sph; S.sph_oi = sph_oi; S.flo_o = flo_o; S.flo_n = flo_n; S.flo_oi = flo_oi;
+    // views are indexed with the global list index
+    S.sph = sph - RR_HEAD_SPHERES; S.sph_oi = sph_oi - RR_HEAD_SPHERES;
+    S.flo_o = flo_o - RR_HEAD_FLOORS; S.flo_n = flo_n - RR_HEAD_FLOORS; S.flo_oi = flo_oi - RR_HEAD_FLOORS;
     return S;
 }
 
 template <bool COUNT, bool F32OUT, bool STAGE>
-__global__ void __launch_bounds__(TRACE_THREADS)
-trace_kernel(const DevScene G, const FrameParams P, void *__restrict__ out, size_t row_stride, Counters *gcnt,
-             int fast_store) {
+__global__ void __launch_bounds__(TRACE_THREADS, RR_TRACE_MIN_BLOCKS)
+trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHead H, const __grid_constant__ FrameParams P,
+             void *__restrict__ out, size_t row_stride, Counters *gcnt, int fast_store, float inv_tiles_x) {
     extern __shared__ float4 rr_smem[];
     const SceneView S = stage_scene(G, rr_smem, STAGE);
 
@@ -58,12 +64,22 @@ trace_kernel(const DevScene G, const FrameParams P, void *__restrict__ out, size
     Counters cnt = {};
 
     for (int tile = gw; tile < ntiles; tile += nw) {
-        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        // ty = tile / tiles_x without an integer division: float estimate + one-step correction
+        // (exact for tile < 2^24; the launcher falls back to inv_tiles_x = 0 -> integer division above that)
+        int ty;
+        if (inv_tiles_x > 0.0f) {
+            ty = (int)(((float)tile + 0.5f) * inv_tiles_x);
+            const int r = tile - ty * tiles_x;
+            ty += (r >= tiles_x) ? 1 : ((r < 0) ? -1 : 0);
+        } else {
+            ty = tile / tiles_x;
+        }
+        const int tx = tile - ty * tiles_x;
         const int x0 = tx << 3, ly0 = ty << 2;
         const int ix = x0 + col, ly = ly0 + row;
         const bool valid = ix < W && ly < rows;
         V3 c = mk(0.0f, 0.0f, 0.0f);
-        if (valid) c = trace_pixel<COUNT>(G, S, P, ix, local_to_image_row(P, ly), cnt);
+        if (valid) c = trace_pixel<COUNT>(G, H, S, P, ix, local_to_image_row(P, ly), cnt);
         if (F32OUT) {
             if (valid) {
                 float *o = reinterpret_cast<float *>(out) + ((size_t)ly * W + ix) * 3;
@@ -78,12 +94,14 @@ trace_kernel(const DevScene G, const FrameParams P, void *__restrict__ out, size
 }
 
 size_t scene_smem_bytes(const DevScene &G) {
-    return (size_t)G.n_spheres * (sizeof(float4) + sizeof(int)) + (size_t)G.n_floors * (2 * sizeof(float4) + sizeof(int)) + 16;
+    const size_t ts = G.n_spheres > RR_HEAD_SPHERES ? G.n_spheres - RR_HEAD_SPHERES : 0;
+    const size_t tf = G.n_floors > RR_HEAD_FLOORS ? G.n_floors - RR_HEAD_FLOORS : 0;
+    return ts * (sizeof(float4) + sizeof(int)) + tf * (2 * sizeof(float4) + sizeof(int)) + 16;
 }
 
 template <bool COUNT, bool F32OUT, bool STAGE>
-static cudaError_t launch_one(const DevScene &G, const FrameParams &P, void *d_out, size_t row_stride, Counters *d_cnt,
-                              cudaStream_t stream, const LaunchInfo &li, size_t smem) {
+static cudaError_t launch_one(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
+                              Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, size_t smem) {
     auto kern = trace_kernel<COUNT, F32OUT, STAGE>;
     cudaError_t e;
     if (smem > 48 * 1024) {
@@ -94,32 +112,34 @@ static cudaError_t launch_one(const DevScene &G, const FrameParams &P, void *d_o
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TRACE_THREADS, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    const int tiles = ((P.xres + 7) / 8) * ((P.local_rows + 3) / 4);
-    const int need = (tiles + (TRACE_THREADS / 32) - 1) / (TRACE_THREADS / 32);
-    int grid = li.sm_count * per_sm;
+    const int tiles_x = (P.xres + 7) / 8;
+    const long long tiles = (long long)tiles_x * ((P.local_rows + 3) / 4);
+    const long long need = (tiles + (TRACE_THREADS / 32) - 1) / (TRACE_THREADS / 32);
+    long long grid = (long long)li.sm_count * per_sm;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     const int fast = (!F32OUT && (P.xres % 8 == 0) && (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0)) ? 1 : 0;
-    kern<<<grid, TRACE_THREADS, smem, stream>>>(G, P, d_out, row_stride, d_cnt, fast);
+    const float inv_tx = tiles < (1 << 24) ? 1.0f / (float)tiles_x : 0.0f;
+    kern<<<(unsigned)grid, TRACE_THREADS, smem, stream>>>(G, H, P, d_out, row_stride, d_cnt, fast, inv_tx);
     return cudaGetLastError();
 }
 
-cudaError_t launch_trace(const DevScene &G, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
-                         Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li) {
+cudaError_t launch_trace(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
+                         bool f32_out, Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li) {
     if (P.xres <= 0 || P.local_rows <= 0) return cudaSuccess;
     size_t smem = scene_smem_bytes(G);
     const bool stage = smem <= li.smem_optin / 2;  // keep >= 2 blocks per SM resident
     if (!stage) smem = 0;
     if (d_cnt) {
-        if (f32_out) return stage ? launch_one<true, true, true>(G, P, d_out, row_stride, d_cnt, stream, li, smem)
-                                  : launch_one<true, true, false>(G, P, d_out, row_stride, d_cnt, stream, li, smem);
-        return stage ? launch_one<true, false, true>(G, P, d_out, row_stride, d_cnt, stream, li, smem)
-                     : launch_one<true, false, false>(G, P, d_out, row_stride, d_cnt, stream, li, smem);
+        if (f32_out) return stage ? launch_one<true, true, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem)
+                                  : launch_one<true, true, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem);
+        return stage ? launch_one<true, false, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem)
+                     : launch_one<true, false, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem);
     }
-    if (f32_out) return stage ? launch_one<false, true, true>(G, P, d_out, row_stride, d_cnt, stream, li, smem)
-                              : launch_one<false, true, false>(G, P, d_out, row_stride, d_cnt, stream, li, smem);
-    return stage ? launch_one<false, false, true>(G, P, d_out, row_stride, d_cnt, stream, li, smem)
-                 : launch_one<false, false, false>(G, P, d_out, row_stride, d_cnt, stream, li, smem);
+    if (f32_out) return stage ? launch_one<false, true, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem)
+                              : launch_one<false, true, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem);
+    return stage ? launch_one<false, false, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem)
+                 : launch_one<false, false, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem);
 }
 
 }  // namespace rr

@@ -1,10 +1,15 @@
 // rr_trace.cuh — ray-trace mode of the per-pixel path (render.rs:993-1224) as device functions.
 //
 // Design (DESIGN.md "trace kernel"):
-//   * scene-level raycast() is a brute-force loop like the reference's, but over two homogeneous
-//     SoA lists (floors, then spheres) staged in shared memory, so the inner loop has no per-object
-//     kind dispatch. Ties are resolved to the lowest ORIGINAL object index, which is what the
+//   * scene-level raycast() is a brute-force scan like the reference's, but over two homogeneous
+//     SoA lists (floors, then spheres), so the inner loop has no per-object kind dispatch. The first
+//     RR_HEAD_FLOORS floors and RR_HEAD_SPHERES spheres travel in the kernel-parameter constant bank
+//     and are tested in a fully unrolled sequence (their coordinates become c[0][..] operands of the
+//     FADD/FMUL instructions: no loads, no registers); the rest of a larger scene is scanned from
+//     shared memory. Ties are resolved to the lowest ORIGINAL object index, which is what the
 //     reference's in-order strict `<` scan does (appendix A Q6).
+//   * one raycast call site: a per-thread state machine alternates "trace ray" and "shadow ray"
+//     phases, so the scan code exists once (I-cache) and lanes in different phases still share it.
 //   * the refraction recursion shading()->raytrace() (render.rs:1093-1115) is unrolled into an
 //     explicit per-thread stack of suspended parent frames; evaluation order of every float sum
 //     is unchanged (the child colour is complete before the parent blends it).
@@ -13,14 +18,14 @@
 
 namespace rr {
 
-// pointers to the intersection lists the hot loops read (shared memory when staged)
+// pointers to the tails of the intersection lists (shared memory when staged)
 struct SceneView {
     const float4 *sph;
     const int *sph_oi;
     const float4 *flo_o;
     const float4 *flo_n;
     const int *flo_oi;
-    int n_spheres, n_floors;
+    int n_spheres, n_floors;  // totals (head + tail)
 };
 
 struct Hit {
@@ -28,68 +33,74 @@ struct Hit {
     int idx;
 };
 
-// RenderFloor::raycast (render.rs:557-569) + RenderSphere::raycast (render.rs:447-471) inside the
-// scene loop of render.rs:993-1018.
-//
-// Sphere algebra: the reference forms b = 2*(eye.wpt), c = wpt.wpt - r*r, d2 = b*b - 4*c,
-// d = sqrt(d2), t0 = (-b - d)/2, t1 = t0 + d. With D = eye.wpt and q = D*D - c this is, exactly
-// (scalings by 2 and 4 commute with IEEE rounding): d2 = 4q, d = 2*sqrt(q), t0 = -D - sqrt(q),
-// t1 = t0 + 2*sqrt(q), and `d2 >= EPSILON` <=> `q >= EPSILON/4`. Same bits, fewer multiplies.
-__device__ __forceinline__ Hit raycast(const SceneView &S, const V3 &vi, const V3 &eye, int ig, unsigned flags) {
-    float t = RR_INF;
-    int idx = 0;
-    for (int f = 0; f < S.n_floors; ++f) {
-        const int oi = S.flo_oi[f];
-        if (oi == ig) continue;
-        const float4 o = S.flo_o[f];
-        const float4 n4 = S.flo_n[f];
-        const V3 n = mk(n4.x, n4.y, n4.z);
-        const V3 wpt = vi - mk(o.x, o.y, o.z);
-        const float w = dot(n, eye);
-        if (w <= 0.0f) {
-            const float t0 = (-dot(n, wpt)) / w;
-            if (t0 >= 0.0f && t0 < t) {  // floors are scanned in index order: strict <
-                t = t0;
+// RenderFloor::raycast, render.rs:557-569, folded into the running minimum of render.rs:1010-1014.
+// Floors are scanned first and in index order, so strict `<` keeps the lowest index.
+__device__ __forceinline__ void floor_test(const float4 &o, const float4 &n4, int oi, const V3 &vi, const V3 &eye,
+                                           int ig, float &t, int &idx) {
+    const V3 n = mk(n4.x, n4.y, n4.z);
+    const V3 wpt = vi - mk(o.x, o.y, o.z);
+    const float w = dot(n, eye);
+    if (w <= 0.0f && oi != ig) {
+        const float t0 = (-dot(n, wpt)) / w;
+        if (t0 >= 0.0f && t0 < t) {
+            t = t0;
+            idx = oi;
+        }
+    }
+}
+
+// RenderSphere::raycast, render.rs:447-471.
+// The reference forms b = 2*(eye.wpt), c = wpt.wpt - r*r, d2 = b*b - 4*c, d = sqrt(d2),
+// t0 = (-b - d)/2, t1 = t0 + d. With D = eye.wpt and q = D*D - c this is, exactly (scalings by 2 and
+// 4 commute with IEEE rounding): d2 = 4q, d = 2*sqrt(q), t0 = -D - sqrt(q), t1 = t0 + 2*sqrt(q), and
+// `d2 >= EPSILON` <=> `q >= EPSILON/4`. Same bits, fewer multiplies.
+template <typename OiFn>
+__device__ __forceinline__ void sphere_test(const float4 &c4, OiFn get_oi, const V3 &vi, const V3 &eye, int ig, bool near_ok,
+                                            bool far_ok, float &t, int &idx) {
+    const V3 wpt = vi - mk(c4.x, c4.y, c4.z);
+    const float D = dot(eye, wpt);
+    const float c = dot(wpt, wpt) - c4.w;
+    const float q = D * D - c;
+    if (q >= F32_EPS_QUARTER) {
+        const float sq = sqrtf(q);
+        const float t0 = -D - sq;
+        float cand = RR_INF;
+        if (near_ok && t0 >= 0.0f) {
+            cand = t0;
+        } else if (far_ok) {
+            const float t1 = t0 + 2.0f * sq;
+            if (0.0f < t1) cand = t1;
+        }
+        if (cand <= t) {
+            // lowest original index wins exact ties (floors were scanned first, spheres are in index order)
+            const int oi = get_oi();  // fetched only for candidates
+            if (oi != ig && (cand < t || (cand < RR_INF && oi < idx))) {
+                t = cand;
                 idx = oi;
             }
         }
     }
-    const bool near_ok = (flags & OUTONLY) == 0;
-    const bool far_ok = (flags & INONLY) == 0;
-    for (int s = 0; s < S.n_spheres; ++s) {
-        const float4 c4 = S.sph[s];
-        const V3 wpt = vi - mk(c4.x, c4.y, c4.z);
-        const float D = dot(eye, wpt);
-        const float c = dot(wpt, wpt) - c4.w;
-        const float q = D * D - c;
-        if (q >= F32_EPS_QUARTER) {
-            const float sq = sqrtf(q);
-            const float t0 = -D - sq;
-            float cand = RR_INF;
-            if (near_ok && t0 >= 0.0f) {
-                cand = t0;
-            } else if (far_ok) {
-                const float t1 = t0 + 2.0f * sq;
-                if (0.0f < t1) cand = t1;
-            }
-            if (cand <= t) {
-                const int oi = S.sph_oi[s];
-                // lowest original index wins exact ties (floors were scanned first)
-                if (oi != ig && (cand < t || (cand < RR_INF && oi < idx))) {
-                    t = cand;
-                    idx = oi;
-                }
-            }
-        }
-    }
-    return Hit{t, idx};
 }
 
-// get_normal — render.rs:443-445 (sphere), :553-555 (floor)
-__device__ __forceinline__ V3 object_normal(const DevScene &G, int idx, const V3 &pt, const float4 &a, int kind) {
-    if (kind == 0) return normalized(pt - mk(a.x, a.y, a.z));
-    const float4 n = __ldg(&G.obj_n[idx]);
-    return mk(n.x, n.y, n.z);
+// scene-level raycast, render.rs:993-1018
+__device__ __forceinline__ Hit raycast(const SceneHead &H, const SceneView &S, const V3 &vi, const V3 &eye, int ig,
+                                       unsigned flags) {
+    float t = RR_INF;
+    int idx = 0;
+#pragma unroll
+    for (int f = 0; f < RR_HEAD_FLOORS; ++f)
+        if (f < S.n_floors) floor_test(H.flo_o[f], H.flo_n[f], H.flo_oi[f], vi, eye, ig, t, idx);
+    for (int f = RR_HEAD_FLOORS; f < S.n_floors; ++f)
+        floor_test(S.flo_o[f], S.flo_n[f], S.flo_oi[f], vi, eye, ig, t, idx);
+    const bool near_ok = (flags & OUTONLY) == 0;
+    const bool far_ok = (flags & INONLY) == 0;
+#pragma unroll
+    for (int s = 0; s < RR_HEAD_SPHERES; ++s)
+        if (s < S.n_spheres) sphere_test(H.sph[s], [&] { return H.sph_oi[s]; }, vi, eye, ig, near_ok, far_ok, t, idx);
+#pragma unroll 4
+    for (int s = RR_HEAD_SPHERES; s < S.n_spheres; ++s)
+        sphere_test(S.sph[s], [&] { return S.sph_oi[s]; }, vi, eye, ig, near_ok, far_ok, t, idx);
+    return Hit{t, idx};
 }
 
 struct TraceFrame {  // a suspended raytrace() frame waiting for its refraction child
@@ -108,9 +119,10 @@ struct TraceFrame {  // a suspended raytrace() frame waiting for its refraction 
 constexpr int RR_MAX_STACK = 32;  // >= max_refractions (checked on the host)
 
 template <bool COUNT>
-__device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneView &S, const FrameParams &P, int ix, int iy,
-                                          Counters &cnt) {
+__device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneHead &H, const SceneView &S, const FrameParams &P,
+                                          int ix, int iy, Counters &cnt) {
     const V3 light = mk(P.light[0], P.light[1], P.light[2]);
+    // current trace ray of the running raytrace() frame
     V3 vi = mk(P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]);
     V3 eye = primary_ray(P, ix, iy);
     int lev = 0, ig = -1, depth = 0;
@@ -118,59 +130,87 @@ __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneView &S,
     V3 ret = mk(0.0f, 0.0f, 0.0f), fcs = mk(1.0f, 1.0f, 1.0f);
     TraceFrame stack[RR_MAX_STACK];
     int ray_class = 0;  // 0 primary, 1 refract child's first ray, 2 reflect continuation
+    // shading() state carried across the shadow ray
+    bool shadow_phase = false;
+    int hidx = 0;
+    V3 pt = vi, n = vi;
+    float diffuse_intensity = 0.0f, reflection_intensity = 0.0f;
     if (COUNT) cnt.pixels++;
 
     for (;;) {
-        lev += 1;  // render.rs:1157
-        if (COUNT) {
-            if (ray_class == 0) cnt.primary++;
-            else if (ray_class == 1) cnt.refract++;
-            else cnt.reflect++;
-            cnt.object_tests += (unsigned long long)(G.n_objects - (ig >= 0 ? 1 : 0));
-            cnt.sphere_tests += (unsigned long long)spheres_tested(G, ig);
+        // ---- the one scene scan: either the frame's trace ray or the shadow ray of a hit ----
+        V3 ro, rd;
+        int rig;
+        unsigned rfl;
+        if (!shadow_phase) {
+            lev += 1;  // render.rs:1157
+            ro = vi; rd = eye; rig = ig; rfl = flags;
+            if (COUNT) {
+                if (ray_class == 0) cnt.primary++;
+                else if (ray_class == 1) cnt.refract++;
+                else cnt.reflect++;
+            }
+        } else {
+            ro = pt + (light * F32_EPSILON);  // render.rs:1034
+            rd = light; rig = hidx; rfl = 0u;
+            if (COUNT) {
+                cnt.shadow++;
+                if (__ldg(&G.obj_b[hidx]).x == 0) cnt.sphere_hits++;
+            }
         }
-        const Hit h = raycast(S, vi, eye, ig, flags);
-        bool frame_done;
-        if (h.t < RR_INF) {
-            const int idx = h.idx;
-            const V3 pt = (eye * h.t) + vi;  // render.rs:1164
+        if (COUNT) {
+            cnt.object_tests += (unsigned long long)(G.n_objects - (rig >= 0 ? 1 : 0));
+            cnt.sphere_tests += (unsigned long long)spheres_tested(G, rig);
+        }
+        const Hit h = raycast(H, S, ro, rd, rig, rfl);
+
+        bool frame_done = false;
+        if (!shadow_phase) {
+            if (h.t < RR_INF) {
+                // hit: first half of shading(), render.rs:1020-1046, then go cast the shadow ray
+                hidx = h.idx;
+                pt = (eye * h.t) + vi;  // render.rs:1164
+                const float4 oa = __ldg(&G.obj_a[hidx]);
+                const int4 ob = __ldg(&G.obj_b[hidx]);
+                if (ob.x == 0) {
+                    n = normalized(pt - mk(oa.x, oa.y, oa.z));  // render.rs:443-445
+                } else {
+                    const float4 n4 = __ldg(&G.obj_n[hidx]);     // render.rs:553-555
+                    n = mk(n4.x, n4.y, n4.z);
+                }
+                const float light_incidence = dot(light, n);
+                const float ln2 = 2.0f * light_incidence;
+                const V3 rr_light = (n * ln2) - light;
+                const int pn = G.mat[ob.z].pn;
+                diffuse_intensity = fmaxf(light_incidence, 0.0f);
+                reflection_intensity = 0.0f;
+                if (pn != 0) {
+                    const float ri = -dot(rr_light, eye);
+                    if (ri > 0.0f) reflection_intensity = rs_powi(ri, pn);
+                }
+                shadow_phase = true;
+                continue;
+            }
+            if (COUNT) cnt.bg_evals++;
+            const V3 bg = bgcolor(P, eye);  // render.rs:1213-1216
+            ret = mk(ret.x + bg.x * fcs.x, ret.y + bg.y * fcs.y, ret.z + bg.z * fcs.z);
+            frame_done = true;
+        } else {
+            // ---- second half of shading(), render.rs:1048-1139 ----
+            shadow_phase = false;
+            const int idx = hidx;
             const float4 oa = __ldg(&G.obj_a[idx]);
             const int4 ob = __ldg(&G.obj_b[idx]);
-            const V3 n = object_normal(G, idx, pt, oa, ob.x);
             const DevMaterial &m = G.mat[ob.z];
-
-            // ---- shading(), render.rs:1020-1140 ----
-            const float light_incidence = dot(light, n);
-            const float ln2 = 2.0f * light_incidence;
-            const V3 rr_light = (n * ln2) - light;
-            const int pn = m.pn;
-            const float diffuse_intensity = fmaxf(light_incidence, 0.0f);
-            const V3 shadow_org = pt + (light * F32_EPSILON);
-            float reflection_intensity = 0.0f;
-            if (pn != 0) {
-                const float ri = -dot(rr_light, eye);
-                if (ri > 0.0f) reflection_intensity = rs_powi(ri, pn);
-            }
             float k1 = 0.2f, k2 = 0.0f;
-            {
-                if (COUNT) {
-                    cnt.shadow++;
-                    cnt.object_tests += (unsigned long long)(G.n_objects - 1);
-                    cnt.sphere_tests += (unsigned long long)spheres_tested(G, idx);
-                    if (ob.x == 0) cnt.sphere_hits++;
-                }
-                const Hit sh = raycast(S, shadow_org, light, idx, 0u);
-                bool lit = sh.t >= RR_INF;
-                if (!lit) lit = 0.0f < G.mat[__ldg(&G.obj_b[sh.idx]).z].t;
-                if (lit) {
-                    k1 = fminf(k1 + diffuse_intensity, 1.0f);
-                    k2 = reflection_intensity;
-                }
+            bool lit = h.t >= RR_INF;
+            if (!lit) lit = 0.0f < G.mat[__ldg(&G.obj_b[h.idx]).z].t;
+            if (lit) {
+                k1 = fminf(k1 + diffuse_intensity, 1.0f);
+                k2 = reflection_intensity;
             }
-            float u, v;
-            get_uv(m, pt - mk(oa.x, oa.y, oa.z), ob.y, u, v);
-            const V3 kd = lookup_texture(G, m, u, v);
-            V3 face = mk(kd.x * k1 + k2, kd.y * k1 + k2, kd.z * k1 + k2);
+            const V3 kd = get_diffuse(G, m, pt - mk(oa.x, oa.y, oa.z), ob.y);
+            const V3 face = mk(kd.x * k1 + k2, kd.y * k1 + k2, kd.z * k1 + k2);
             const V3 ks = mk(m.specular[0], m.specular[1], m.specular[2]);
 
             if (lev < P.max_refractions && 0.0f < m.t) {
@@ -208,7 +248,7 @@ __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneView &S,
                 ret = mk(0.0f, 0.0f, 0.0f);
                 fcs = mk(1.0f, 1.0f, 1.0f);
                 ray_class = 1;
-                continue;  // child starts with lev = nest; the loop head increments it
+                continue;  // child starts with lev = nest; the trace phase increments it
             }
 
             // ---- back in raytrace(), render.rs:1173-1211 ----
@@ -223,13 +263,7 @@ __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneView &S,
                 flags = dot(n, eye) < 0.0f ? OUTONLY : INONLY;
                 ig = idx;
                 ray_class = 2;
-                frame_done = false;
             }
-        } else {
-            if (COUNT) cnt.bg_evals++;
-            const V3 bg = bgcolor(P, eye);  // render.rs:1213-1216
-            ret = mk(ret.x + bg.x * fcs.x, ret.y + bg.y * fcs.y, ret.z + bg.z * fcs.z);
-            frame_done = true;
         }
 
         // return from finished frames into their suspended parents (render.rs:1128-1132 then :1175-1211)

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libray_rust_b200.so")
+# RAY_RUST_B200_LIB selects another build of the same library (A/B runs of kernel variants)
+LIB_PATH = os.environ.get("RAY_RUST_B200_LIB") or os.path.join(_HERE, "libray_rust_b200.so")
 
 RR_OK = 0
 RR_ERR_BAD_ARG = -1

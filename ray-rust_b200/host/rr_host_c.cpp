@@ -1,0 +1,95 @@
+// rr_host_c.cpp — small extern "C" facade over the C++ host layer so the Python tests can drive it
+// (scene construction, YAML round trips, flattening) without a GPU.
+#include <cstring>
+
+#include "rr_host.hpp"
+
+namespace {
+thread_local std::string g_err;
+char *dup(const std::string &s) {
+    char *p = (char *)malloc(s.size() + 1);
+    memcpy(p, s.c_str(), s.size() + 1);
+    return p;
+}
+struct Handle {
+    rr::RenderEnv ren;
+    rr::FlatScene flat;
+};
+}  // namespace
+
+extern "C" {
+
+const char *rrh_last_error() { return g_err.c_str(); }
+void rrh_free(void *p) { free(p); }
+
+// kind: 0 = default scene (main.rs:154-276), 1 = synthetic scene (n_spheres, seed)
+void *rrh_env_new(int kind, int width, int height, int raymarch, int glow_some, float glow, int n_spheres, uint64_t seed) {
+    try {
+        rr::RenderEnv ren = kind == 0 ? rr::default_scene(width, height, raymarch != 0, glow_some != 0, glow)
+                                      : rr::synthetic_scene(width, height, n_spheres, seed);
+        if (kind != 0) ren.use_raymarching(raymarch != 0).glow_effect(glow_some != 0, glow);
+        return new Handle{std::move(ren), {}};
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void rrh_env_free(void *h) { delete (Handle *)h; }
+char *rrh_env_serialize(void *h) { return dup(((Handle *)h)->ren.serialize()); }
+int rrh_env_deserialize(void *h, const char *text) {
+    try {
+        ((Handle *)h)->ren.deserialize(text);
+        return 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+// flatten into the handle; returns pointers valid until the next call / free
+int rrh_env_flatten(void *h, rr_scene_desc *desc, rr_frame_params *params) {
+    Handle *H = (Handle *)h;
+    H->flat = rr::flatten(H->ren);
+    *desc = H->flat.desc();
+    *params = H->ren.frame_params();
+    return 0;
+}
+int rrh_env_limits(void *h, int *max_reflections, int *max_refractions, int *n_keyframes) {
+    Handle *H = (Handle *)h;
+    *max_reflections = H->ren.max_reflections;
+    *max_refractions = H->ren.max_refractions;
+    *n_keyframes = (int)H->ren.camera_motion.size();
+    return 0;
+}
+// render through the C++ render() signature: pointproc is invoked once per pixel
+typedef void (*rrh_pointproc)(int x, int y, float r, float g, float b, void *user);
+int rrh_render(void *h, rrh_pointproc cb, void *user, int thread_count) {
+    try {
+        rr::render(((Handle *)h)->ren, [&](int x, int y, const rr::RenderColor &c) { cb(x, y, c.r, c.g, c.b, user); }, thread_count);
+        return 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+int rrh_render_rgb8(void *h, uint8_t *out) {
+    try {
+        rr::render_rgb8(((Handle *)h)->ren, out);
+        return 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+int rrh_png_roundtrip(const uint8_t *rgb, uint32_t w, uint32_t h, const char *path, uint8_t *back) {
+    try {
+        rr::save_png_rgb8(path, rgb, w, h);
+        auto t = rr::load_png_rgb8(path);
+        if (!t || t->width != w || t->height != h) return -2;
+        memcpy(back, t->rgb8.data(), (size_t)w * h * 3);
+        return 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+}

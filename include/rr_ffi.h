@@ -162,7 +162,12 @@ int rr_device_count(int *count);
 int rr_scene_create(const rr_scene_desc *desc, int device, rr_scene **out);
 int rr_scene_destroy(rr_scene *scene);
 
-/* Size in bytes of the packed RGB8 output for `params` (all rows, or this shard's rows). */
+/* Large scenes (>= 24 spheres) are rendered through an exact culling structure (a BVH whose leaf test
+ * is the reference's sphere test; results are bit-identical to the brute-force scan). enabled=0 forces
+ * the brute-force scan of render.rs:993-1018 (used by tests to compare the two on the device). */
+int rr_scene_set_culling(rr_scene *scene, int enabled);
+
+/* Number of rows a call with `params` produces (all rows, or this shard's bands). */
 int rr_frame_rows(const rr_frame_params *params, int32_t *rows_out);
 
 /* render(): RGB8, result in HOST memory. Replaces `render(&ren, &mut putpoint, threads)` +

@@ -6,6 +6,8 @@
 // here: every render entry point either runs the CUDA kernels or fails.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -55,6 +57,7 @@ struct rr_scene {
     cudaEvent_t chunk_ev[8] = {};
     float last_ms = 0.0f;
     bool timed = false;
+    bool culling = true;
 };
 
 namespace {
@@ -115,9 +118,73 @@ rr::FrameParams to_dev(const rr_frame_params *p) {
 int launch(rr_scene *s, const rr::FrameParams &P, void *d_out, size_t row_stride, bool f32, rr::Counters *d_cnt,
            cudaStream_t st) {
     cudaError_t e = P.use_raymarching ? rr::launch_march(s->G, P, d_out, row_stride, f32, d_cnt, s->d_work, st, s->li)
-                                      : rr::launch_trace(s->G, s->H, P, d_out, row_stride, f32, d_cnt, st, s->li);
+                                      : rr::launch_trace(s->G, s->H, P, d_out, row_stride, f32, d_cnt, st, s->li, s->culling);
     if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
     return RR_OK;
+}
+
+// ---- BVH over the spheres (host build, depth-first layout with escape indices) --------------------
+struct Bvh {
+    std::vector<float4> a, b;  // node arrays, see DevScene
+    std::vector<int> order;    // sphere list index in leaf order
+    float lo[3], hi[3], r_min;
+};
+
+void build_node(const std::vector<float4> &sph, std::vector<int> &idx, int begin, int end, Bvh &out) {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = begin; i < end; ++i) {
+        const float4 &s = sph[idx[i]];
+        const float c[3] = {s.x, s.y, s.z};
+        const float r = std::fabs(s.w);
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = std::fmin(lo[k], c[k] - r); hi[k] = std::fmax(hi[k], c[k] + r);
+            clo[k] = std::fmin(clo[k], c[k]); chi[k] = std::fmax(chi[k], c[k]);
+        }
+    }
+    const size_t me = out.a.size();
+    out.a.push_back(make_float4(lo[0], lo[1], lo[2], 0.0f));
+    out.b.push_back(make_float4(hi[0], hi[1], hi[2], 0.0f));
+    const int count = end - begin;
+    int leaf = -1;
+    if (count <= rr::RR_BVH_LEAF) {
+        leaf = ((int)out.order.size() << 3) | count;
+        for (int i = begin; i < end; ++i) out.order.push_back(idx[i]);
+    } else {
+        int axis = 0;
+        for (int k = 1; k < 3; ++k) if (chi[k] - clo[k] > chi[axis] - clo[axis]) axis = k;
+        const int mid = begin + count / 2;
+        std::nth_element(idx.begin() + begin, idx.begin() + mid, idx.begin() + end, [&](int p, int q) {
+            const float cp = axis == 0 ? sph[p].x : axis == 1 ? sph[p].y : sph[p].z;
+            const float cq = axis == 0 ? sph[q].x : axis == 1 ? sph[q].y : sph[q].z;
+            return cp < cq || (cp == cq && p < q);
+        });
+        build_node(sph, idx, begin, mid, out);
+        build_node(sph, idx, mid, end, out);
+    }
+    const int escape = (int)out.a.size();  // first node after this subtree
+    std::memcpy(&out.a[me].w, &escape, sizeof(int));
+    std::memcpy(&out.b[me].w, &leaf, sizeof(int));
+}
+
+// sph_m: (cx, cy, cz, r). Returns false when no BVH should be used (few spheres, non-finite data).
+bool build_bvh(const std::vector<float4> &sph_m, Bvh &out) {
+    const int n = (int)sph_m.size();
+    if (n < rr::RR_BVH_MIN_SPHERES || n >= (1 << 27)) return false;
+    float rmin = INFINITY;
+    for (const float4 &s : sph_m) {
+        if (!std::isfinite(s.x) || !std::isfinite(s.y) || !std::isfinite(s.z) || !std::isfinite(s.w)) return false;
+        rmin = std::fmin(rmin, std::fabs(s.w));
+    }
+    std::vector<int> idx(n);
+    for (int i = 0; i < n; ++i) idx[i] = i;
+    build_node(sph_m, idx, 0, n, out);
+    for (int k = 0; k < 3; ++k) {
+        out.lo[k] = k == 0 ? out.a[0].x : k == 1 ? out.a[0].y : out.a[0].z;
+        out.hi[k] = k == 0 ? out.b[0].x : k == 1 ? out.b[0].y : out.b[0].z;
+    }
+    out.r_min = rmin;
+    return true;
 }
 
 int ensure_out(rr_scene *s, size_t bytes) {
@@ -244,6 +311,25 @@ int rr_scene_create(const rr_scene_desc *desc, int device, rr_scene **out) {
         (rc = upload(s, flo_oi, &G.flo_oi)) || (rc = upload(s, obj_a, &G.obj_a)) || (rc = upload(s, obj_n, &G.obj_n)) ||
         (rc = upload(s, obj_b, &G.obj_b)) || (rc = upload(s, mats, &G.mat)) || (rc = upload(s, tex, &G.tex)))
         return bail(rc);
+
+    // exact culling structure for large scenes (rr_trace.cuh "BVH")
+    {
+        Bvh bvh;
+        if (build_bvh(sph_m, bvh)) {
+            std::vector<float4> bsph, bsph_m;
+            std::vector<int> boi;
+            std::vector<float> bglow;
+            for (int k : bvh.order) {
+                bsph.push_back(sph[k]); bsph_m.push_back(sph_m[k]); boi.push_back(sph_oi[k]); bglow.push_back(sph_glow[k]);
+            }
+            if ((rc = upload(s, bvh.a, &G.bvh_a)) || (rc = upload(s, bvh.b, &G.bvh_b)) || (rc = upload(s, bsph, &G.bsph)) ||
+                (rc = upload(s, bsph_m, &G.bsph_m)) || (rc = upload(s, boi, &G.bsph_oi)) || (rc = upload(s, bglow, &G.bsph_glow)))
+                return bail(rc);
+            G.n_bvh_nodes = (int)bvh.a.size();
+            for (int c = 0; c < 3; ++c) { G.scene_lo[c] = bvh.lo[c]; G.scene_hi[c] = bvh.hi[c]; }
+            G.r_min = bvh.r_min;
+        }
+    }
 
     for (int k = 0; k < rr::RR_HEAD_SPHERES && k < (int)sph.size(); ++k) { s->H.sph[k] = sph[k]; s->H.sph_oi[k] = sph_oi[k]; }
     for (int k = 0; k < rr::RR_HEAD_FLOORS && k < (int)flo_o.size(); ++k) {
@@ -415,6 +501,13 @@ int rr_bands_unpack_device(const rr_frame_params *params, const void *d_packed, 
     cudaError_t e = rr::launch_bands_unpack(P, d_packed, shard_stride_bytes, d_frame, reinterpret_cast<cudaStream_t>(cuda_stream));
     if (e != cudaSuccess) return fail_cuda(e, "bands_unpack");
     if (!cuda_stream) CU(cudaStreamSynchronize(nullptr));
+    return RR_OK;
+}
+
+int rr_scene_set_culling(rr_scene *s, int enabled) {
+    if (!s) return fail(RR_ERR_BAD_ARG, "scene is null");
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->culling = enabled != 0;
     return RR_OK;
 }
 

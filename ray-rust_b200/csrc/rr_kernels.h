@@ -14,13 +14,10 @@ struct LaunchInfo {
     size_t smem_optin;  // max opt-in dynamic shared memory per block
 };
 
-// bytes of dynamic shared memory needed to stage the intersection lists of `G`
-size_t scene_smem_bytes(const DevScene &G);
-
 // Ray-trace mode. d_out: RGB8 (row_stride bytes per row) or, when f32_out, packed float rgb.
 // d_cnt != nullptr selects the instrumented instantiation.
 cudaError_t launch_trace(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
-                         Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li);
+                         Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh);
 // Ray-march mode (same contract). d_work: one unsigned int work counter (zeroed by the launcher).
 cudaError_t launch_march(const DevScene &G, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
                          Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li);

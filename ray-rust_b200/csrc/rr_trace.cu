@@ -3,7 +3,7 @@
 //
 // Mapping: a warp owns an 8x4 pixel tile (coherent primary rays, 24-byte row runs for the RGB8
 // store); warps walk the tile list with a static grid stride from a persistent grid of
-// (SM count x resident blocks), so the scene tail is staged into shared memory once per block.
+// (SM count x resident blocks), so the scene is staged into shared memory once per block.
 // The kernel is FP32-ALU / divergence bound: compiled with -fmad=false for bit parity, no tensor
 // cores, DRAM traffic = the framebuffer store only.
 #include "rr_kernels.h"
@@ -16,42 +16,59 @@ constexpr int TRACE_THREADS = 256;
 #define RR_TRACE_MIN_BLOCKS 4
 #endif
 
-// Only the list tails (objects beyond the SceneHead) are staged; small scenes stage nothing.
+template <typename T>
+__device__ __forceinline__ void copy_list(T *dst, const T *src, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+// Stage what the scan loops read into shared memory: the list tails (objects beyond the SceneHead)
+// for the brute-force scan, or the BVH nodes + leaf-ordered spheres. Small scenes stage nothing.
+template <bool BVH>
 __device__ __forceinline__ SceneView stage_scene(const DevScene &G, float4 *smem, bool stage) {
     SceneView S;
     S.n_spheres = G.n_spheres;
     S.n_floors = G.n_floors;
     S.sph = G.sph; S.sph_oi = G.sph_oi; S.flo_o = G.flo_o; S.flo_n = G.flo_n; S.flo_oi = G.flo_oi;
+    S.bvh_a = G.bvh_a; S.bvh_b = G.bvh_b; S.bsph = G.bsph; S.bsph_oi = G.bsph_oi; S.n_bvh_nodes = G.n_bvh_nodes;
     if (!stage) return S;
-    const int ts = max(G.n_spheres - RR_HEAD_SPHERES, 0), tf = max(G.n_floors - RR_HEAD_FLOORS, 0);
-    if (ts + tf == 0) return S;
-    float4 *sph = smem;
-    float4 *flo_o = sph + ts;
-    float4 *flo_n = flo_o + tf;
-    int *sph_oi = reinterpret_cast<int *>(flo_n + tf);
-    int *flo_oi = sph_oi + ts;
-    for (int i = threadIdx.x; i < ts; i += blockDim.x) {
-        sph[i] = G.sph[RR_HEAD_SPHERES + i];
-        sph_oi[i] = G.sph_oi[RR_HEAD_SPHERES + i];
-    }
-    for (int i = threadIdx.x; i < tf; i += blockDim.x) {
-        flo_o[i] = G.flo_o[RR_HEAD_FLOORS + i];
-        flo_n[i] = G.flo_n[RR_HEAD_FLOORS + i];
-        flo_oi[i] = G.flo_oi[RR_HEAD_FLOORS + i];
-    }
+    const int tf = max(G.n_floors - RR_HEAD_FLOORS, 0);
+    const int ts = BVH ? 0 : max(G.n_spheres - RR_HEAD_SPHERES, 0);
+    const int nb = BVH ? G.n_bvh_nodes : 0, bs = BVH ? G.n_spheres : 0;
+    if (ts + tf + nb == 0) return S;
+    float4 *p = smem;
+    float4 *sph = p; p += ts;
+    float4 *flo_o = p; p += tf;
+    float4 *flo_n = p; p += tf;
+    float4 *bvh_a = p; p += nb;
+    float4 *bvh_b = p; p += nb;
+    float4 *bsph = p; p += bs;
+    int *q = reinterpret_cast<int *>(p);
+    int *sph_oi = q; q += ts;
+    int *flo_oi = q; q += tf;
+    int *bsph_oi = q;
+    copy_list(sph, G.sph + RR_HEAD_SPHERES, ts);
+    copy_list(sph_oi, G.sph_oi + RR_HEAD_SPHERES, ts);
+    copy_list(flo_o, G.flo_o + RR_HEAD_FLOORS, tf);
+    copy_list(flo_n, G.flo_n + RR_HEAD_FLOORS, tf);
+    copy_list(flo_oi, G.flo_oi + RR_HEAD_FLOORS, tf);
+    copy_list(bvh_a, G.bvh_a, nb);
+    copy_list(bvh_b, G.bvh_b, nb);
+    copy_list(bsph, G.bsph, bs);
+    copy_list(bsph_oi, G.bsph_oi, bs);
     __syncthreads();
-    // views are indexed with the global list index
+    // tail views are indexed with the global list index
     S.sph = sph - RR_HEAD_SPHERES; S.sph_oi = sph_oi - RR_HEAD_SPHERES;
     S.flo_o = flo_o - RR_HEAD_FLOORS; S.flo_n = flo_n - RR_HEAD_FLOORS; S.flo_oi = flo_oi - RR_HEAD_FLOORS;
+    if (BVH) { S.bvh_a = bvh_a; S.bvh_b = bvh_b; S.bsph = bsph; S.bsph_oi = bsph_oi; }
     return S;
 }
 
-template <bool COUNT, bool F32OUT, bool STAGE>
+template <bool COUNT, bool F32OUT, bool STAGE, bool BVH>
 __global__ void __launch_bounds__(TRACE_THREADS, RR_TRACE_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHead H, const __grid_constant__ FrameParams P,
              void *__restrict__ out, size_t row_stride, Counters *gcnt, int fast_store, float inv_tiles_x) {
     extern __shared__ float4 rr_smem[];
-    const SceneView S = stage_scene(G, rr_smem, STAGE);
+    const SceneView S = stage_scene<BVH>(G, rr_smem, STAGE);
 
     const int W = P.xres, rows = P.local_rows;
     const int tiles_x = (W + 7) >> 3, tiles_y = (rows + 3) >> 2;
@@ -79,7 +96,7 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
         const int ix = x0 + col, ly = ly0 + row;
         const bool valid = ix < W && ly < rows;
         V3 c = mk(0.0f, 0.0f, 0.0f);
-        if (valid) c = trace_pixel<COUNT>(G, H, S, P, ix, local_to_image_row(P, ly), cnt);
+        if (valid) c = trace_pixel<COUNT, BVH>(G, H, S, P, ix, local_to_image_row(P, ly), cnt);
         if (F32OUT) {
             if (valid) {
                 float *o = reinterpret_cast<float *>(out) + ((size_t)ly * W + ix) * 3;
@@ -93,16 +110,18 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
     if (COUNT) flush_counters(cnt, gcnt);
 }
 
-size_t scene_smem_bytes(const DevScene &G) {
-    const size_t ts = G.n_spheres > RR_HEAD_SPHERES ? G.n_spheres - RR_HEAD_SPHERES : 0;
+static size_t trace_smem_bytes(const DevScene &G, bool bvh) {
     const size_t tf = G.n_floors > RR_HEAD_FLOORS ? G.n_floors - RR_HEAD_FLOORS : 0;
-    return ts * (sizeof(float4) + sizeof(int)) + tf * (2 * sizeof(float4) + sizeof(int)) + 16;
+    size_t b = tf * (2 * sizeof(float4) + sizeof(int)) + 16;
+    if (bvh) return b + (size_t)G.n_bvh_nodes * 2 * sizeof(float4) + (size_t)G.n_spheres * (sizeof(float4) + sizeof(int));
+    const size_t ts = G.n_spheres > RR_HEAD_SPHERES ? G.n_spheres - RR_HEAD_SPHERES : 0;
+    return b + ts * (sizeof(float4) + sizeof(int));
 }
 
-template <bool COUNT, bool F32OUT, bool STAGE>
+template <bool COUNT, bool F32OUT, bool STAGE, bool BVH>
 static cudaError_t launch_one(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
                               Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, size_t smem) {
-    auto kern = trace_kernel<COUNT, F32OUT, STAGE>;
+    auto kern = trace_kernel<COUNT, F32OUT, STAGE, BVH>;
     cudaError_t e;
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -124,22 +143,26 @@ static cudaError_t launch_one(const DevScene &G, const SceneHead &H, const Frame
     return cudaGetLastError();
 }
 
-cudaError_t launch_trace(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
-                         bool f32_out, Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li) {
-    if (P.xres <= 0 || P.local_rows <= 0) return cudaSuccess;
-    size_t smem = scene_smem_bytes(G);
+template <bool COUNT, bool F32OUT>
+static cudaError_t launch_two(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
+                              Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh) {
+    const bool bvh = allow_bvh && G.n_bvh_nodes > 0;
+    size_t smem = trace_smem_bytes(G, bvh);
     const bool stage = smem <= li.smem_optin / 2;  // keep >= 2 blocks per SM resident
     if (!stage) smem = 0;
-    if (d_cnt) {
-        if (f32_out) return stage ? launch_one<true, true, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem)
-                                  : launch_one<true, true, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem);
-        return stage ? launch_one<true, false, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem)
-                     : launch_one<true, false, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem);
-    }
-    if (f32_out) return stage ? launch_one<false, true, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem)
-                              : launch_one<false, true, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem);
-    return stage ? launch_one<false, false, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem)
-                 : launch_one<false, false, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem);
+    if (bvh) return stage ? launch_one<COUNT, F32OUT, true, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem)
+                          : launch_one<COUNT, F32OUT, false, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem);
+    return stage ? launch_one<COUNT, F32OUT, true, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem)
+                 : launch_one<COUNT, F32OUT, false, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem);
+}
+
+cudaError_t launch_trace(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
+                         bool f32_out, Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh) {
+    if (P.xres <= 0 || P.local_rows <= 0) return cudaSuccess;
+    if (d_cnt) return f32_out ? launch_two<true, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, allow_bvh)
+                              : launch_two<true, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, allow_bvh);
+    return f32_out ? launch_two<false, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, allow_bvh)
+                   : launch_two<false, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, allow_bvh);
 }
 
 }  // namespace rr

@@ -26,6 +26,10 @@ struct SceneView {
     const float4 *flo_n;
     const int *flo_oi;
     int n_spheres, n_floors;  // totals (head + tail)
+    // BVH mode (scenes with many spheres): nodes and the leaf-ordered sphere copy
+    const float4 *bvh_a, *bvh_b, *bsph;
+    const int *bsph_oi;
+    int n_bvh_nodes;
 };
 
 struct Hit {
@@ -82,9 +86,72 @@ __device__ __forceinline__ void sphere_test(const float4 &c4, OiFn get_oi, const
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// BVH: an EXACT cull for scenes with many spheres. The reference scans every object; a sphere may
+// be skipped only if its (f32, reference-order) test provably cannot change the result, i.e. it
+// returns a miss or a candidate t strictly greater than the current best. The leaf test is the
+// same bit-exact sphere_test(); only the decision to skip uses other arithmetic, with margins:
+//   * rounding analysis of the reference's q = D*D - (wpt.wpt - r*r): |q_f32 - q_true| <= 21 u d^2
+//     (u = 2^-24, d = |origin - centre|), so a sphere the f32 test can hit lies within
+//     sqrt(r^2 + K d^2) of the ray with K = 1.25e-6. Boxes are inflated per ray by
+//     e = sqrt(r_min^2 + M D^2) - r_min + 1e-6 D, M = 6e-6 (4.8 K), D = largest distance from the ray
+//     origin to the scene bounds; the same inflation bounds |t_f32 - t_true| for the entry test.
+//   * slab arithmetic itself gets 1e-6 relative slack on both interval ends.
+// Ties keep the reference rule (lowest original index) because leaves apply the full lexicographic
+// comparison whatever the visiting order. Verified bit-for-bit against the brute-force oracle in
+// tests/test_parity_gpu.py (synthetic scenes, all depth limits) and against the brute-force
+// kernel instance in tests/test_bvh_gpu.py.
+// ---------------------------------------------------------------------------------------------
+constexpr float RR_BVH_M = 6e-6f;
+
+__device__ __forceinline__ void bvh_scan(const DevScene &G, const SceneView &S, const V3 &vi, const V3 &eye, int ig,
+                                         bool near_ok, bool far_ok, float &t, int &idx) {
+    // per-ray inflation (fast math is fine here: these values only gate which exact tests run)
+    const float Dx = fmaxf(fabsf(vi.x - G.scene_lo[0]), fabsf(vi.x - G.scene_hi[0]));
+    const float Dy = fmaxf(fabsf(vi.y - G.scene_lo[1]), fabsf(vi.y - G.scene_hi[1]));
+    const float Dz = fmaxf(fabsf(vi.z - G.scene_lo[2]), fabsf(vi.z - G.scene_hi[2]));
+    const float D2 = __fmaf_rn(Dx, Dx, __fmaf_rn(Dy, Dy, Dz * Dz));
+    const float D = sqrtf(D2);
+    const float e = sqrtf(__fmaf_rn(RR_BVH_M, D2, G.r_min * G.r_min)) - G.r_min + 1e-6f * D;
+    // a zero direction component would give 0*inf = NaN in the slab products; nudge it (cull-only arithmetic)
+    const float ex = fabsf(eye.x) < 1e-30f ? copysignf(1e-30f, eye.x) : eye.x;
+    const float ey = fabsf(eye.y) < 1e-30f ? copysignf(1e-30f, eye.y) : eye.y;
+    const float ez = fabsf(eye.z) < 1e-30f ? copysignf(1e-30f, eye.z) : eye.z;
+    const float ix = __frcp_rn(ex), iy = __frcp_rn(ey), iz = __frcp_rn(ez);
+    // origin shifted so each slab bound is one subtraction: (lo - e - o) = lo - (o + e)
+    const float ox_lo = vi.x + e, oy_lo = vi.y + e, oz_lo = vi.z + e;
+    const float ox_hi = vi.x - e, oy_hi = vi.y - e, oz_hi = vi.z - e;
+    int node = 0;
+    const int n = S.n_bvh_nodes;
+    while (node < n) {
+        const float4 a = S.bvh_a[node];
+        const float4 b = S.bvh_b[node];
+        const float t1x = (a.x - ox_lo) * ix, t2x = (b.x - ox_hi) * ix;
+        const float t1y = (a.y - oy_lo) * iy, t2y = (b.y - oy_hi) * iy;
+        const float t1z = (a.z - oz_lo) * iz, t2z = (b.z - oz_hi) * iz;
+        const float tmin = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fminf(t1z, t2z));
+        const float tmax = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fmaxf(t1z, t2z));
+        const float tmin_lo = tmin - fabsf(tmin) * 1e-6f;
+        const float tmax_hi = tmax + fabsf(tmax) * 1e-6f;
+        const bool reject = (tmax_hi < tmin_lo) || (tmax_hi < 0.0f) || (tmin_lo > t);
+        const int leaf = __float_as_int(b.w);
+        if (reject) {
+            node = __float_as_int(a.w);  // escape: skip the subtree
+        } else if (leaf < 0) {
+            node = node + 1;             // descend (depth-first order: the left child is next)
+        } else {
+            const int first = leaf >> 3, count = leaf & 7;
+            for (int k = 0; k < count; ++k)
+                sphere_test(S.bsph[first + k], [&] { return S.bsph_oi[first + k]; }, vi, eye, ig, near_ok, far_ok, t, idx);
+            node = __float_as_int(a.w);
+        }
+    }
+}
+
 // scene-level raycast, render.rs:993-1018
-__device__ __forceinline__ Hit raycast(const SceneHead &H, const SceneView &S, const V3 &vi, const V3 &eye, int ig,
-                                       unsigned flags) {
+template <bool BVH>
+__device__ __forceinline__ Hit raycast(const DevScene &G, const SceneHead &H, const SceneView &S, const V3 &vi, const V3 &eye,
+                                       int ig, unsigned flags) {
     float t = RR_INF;
     int idx = 0;
 #pragma unroll
@@ -94,6 +161,10 @@ __device__ __forceinline__ Hit raycast(const SceneHead &H, const SceneView &S, c
         floor_test(S.flo_o[f], S.flo_n[f], S.flo_oi[f], vi, eye, ig, t, idx);
     const bool near_ok = (flags & OUTONLY) == 0;
     const bool far_ok = (flags & INONLY) == 0;
+    if (BVH) {
+        bvh_scan(G, S, vi, eye, ig, near_ok, far_ok, t, idx);
+        return Hit{t, idx};
+    }
 #pragma unroll
     for (int s = 0; s < RR_HEAD_SPHERES; ++s)
         if (s < S.n_spheres) sphere_test(H.sph[s], [&] { return H.sph_oi[s]; }, vi, eye, ig, near_ok, far_ok, t, idx);
@@ -118,7 +189,7 @@ struct TraceFrame {  // a suspended raytrace() frame waiting for its refraction 
 
 constexpr int RR_MAX_STACK = 32;  // >= max_refractions (checked on the host)
 
-template <bool COUNT>
+template <bool COUNT, bool BVH>
 __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneHead &H, const SceneView &S, const FrameParams &P,
                                           int ix, int iy, Counters &cnt) {
     const V3 light = mk(P.light[0], P.light[1], P.light[2]);
@@ -162,7 +233,7 @@ __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneHead &H,
             cnt.object_tests += (unsigned long long)(G.n_objects - (rig >= 0 ? 1 : 0));
             cnt.sphere_tests += (unsigned long long)spheres_tested(G, rig);
         }
-        const Hit h = raycast(H, S, ro, rd, rig, rfl);
+        const Hit h = raycast<BVH>(G, H, S, ro, rd, rig, rfl);
 
         bool frame_done = false;
         if (!shadow_phase) {

@@ -118,6 +118,7 @@ PROTOTYPES = {
     "rr_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "rr_scene_create": (C.c_int, [C.POINTER(rr_scene_desc), C.c_int, C.POINTER(_P)]),
     "rr_scene_destroy": (C.c_int, [_P]),
+    "rr_scene_set_culling": (C.c_int, [_P, C.c_int]),
     "rr_frame_rows": (C.c_int, [C.POINTER(rr_frame_params), C.POINTER(C.c_int32)]),
     "rr_render_rgb8": (C.c_int, [_P, C.POINTER(rr_frame_params), _P, C.c_size_t]),
     "rr_render_f32": (C.c_int, [_P, C.POINTER(rr_frame_params), _P]),

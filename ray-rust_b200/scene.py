@@ -459,6 +459,10 @@ class DeviceScene:
         except Exception:
             pass
 
+    def set_culling(self, enabled):
+        """enabled=False forces the brute-force object scan (tests compare it with the BVH path)."""
+        ffi.check(self.lib.rr_scene_set_culling(self.handle, 1 if enabled else 0))
+
     def render_rgb8(self, params, out=None):
         rows = frame_rows(params)
         if out is None:

@@ -6,17 +6,21 @@
 
 A "step" renders one whole frame of the workload:
   N=1  "default-4k-trace"  = BASELINE.json configs[1]: built-in scene, 3840x2160, ray-trace mode.
-  N>1  "default-8k-trace-bands" = configs[4]: built-in scene, 7680x4320, interleaved 16-row bands
-       over the N ranks, bands gathered to rank 0 over NCCL and un-interleaved there.
-`value` = reference-equivalent rays (one ray = one scene-level raycast(); counted by
-the instrumented kernel and checked against the oracle in tests/) per second of device time with the
-scene resident in HBM; `e2e` = same through rr_render_rgb8 into pinned HOST memory (wall clock,
-includes the D2H of the frame). The reference arm (--impl reference) times the CPU oracle
-(oracle/, the C++ restatement of the reference: no Rust toolchain exists here) on all host cores.
+  N>1  "default-8k-trace-bands" = configs[4]: built-in scene, 7680x4320, interleaved 16-row bands over
+       the N ranks (one process per GPU). Every rank's render kernel stores its rows straight into rank 0's
+       frame over NVLink peer memory (CUDA IPC); the step ends with a 1-element NCCL all-reduce that orders
+       completion. The NCCL-gather + un-interleave alternative is timed too and reported under "alt".
+`value` = reference-equivalent rays (one ray = one scene-level raycast(); counted by the
+instrumented kernel and checked against the oracle in tests/) per second of device time with the scene
+resident in HBM; `e2e` = same through the C ABI into HOST memory (wall clock, includes the D2H of the
+frame; for N>1 each rank copies its bands into one shared page-locked host frame over its own PCIe link).
+The reference arm (--impl reference) times the CPU oracle (oracle/, the C++ restatement of the reference:
+no Rust toolchain exists here) on all host cores.
 """
 import argparse
 import ctypes as C
 import json
+import mmap
 import os
 import statistics
 import sys
@@ -109,7 +113,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.002)
 
     def stop(self):
         self._stop_evt.set()
@@ -181,13 +185,14 @@ def main():
         args.steps = args.steps or 10
         args.warmup = 1 if args.warmup is None else args.warmup
         return run_reference(args)
-    args.steps = args.steps or 50
+    args.steps = args.steps or 100
     args.warmup = 5 if args.warmup is None else max(3, args.warmup)
 
     import numpy as np
     import torch
 
     import ray_rust_b200 as rr
+    from ray_rust_b200 import bands
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -211,8 +216,9 @@ def main():
     sharded = world > 1
     p = ren.frame_params(BAND_ROWS, rank, world) if sharded else ren.frame_params()
     my_rows = rr.frame_rows(p)
-    max_rows = max(rr.frame_rows(ren.frame_params(BAND_ROWS, r, world)) for r in range(world)) if sharded else H
+    max_rows = bands.max_shard_rows(H, BAND_ROWS, world) if sharded else H
     shard_bytes = max_rows * W * 3
+    frame_bytes = H * W * 3
 
     # ---- ray counts of the whole frame (reference-equivalent; instrumented kernel, untimed) ----
     _, cnt = scene.render_count(ren.frame_params(), want_image=False)
@@ -221,88 +227,172 @@ def main():
     flops = algorithmic_flops(counts, march)
 
     stream = torch.cuda.current_stream(dev)
-    out = torch.empty(shard_bytes, dtype=torch.uint8, device=dev)
-    gathered = torch.empty(world * shard_bytes, dtype=torch.uint8, device=dev) if (sharded and rank == 0) else None
-    frame = torch.empty(H * W * 3, dtype=torch.uint8, device=dev) if (sharded and rank == 0) else None
+    sptr = C.c_void_p(stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    launches = 0
-
-    def step():
-        n = 1
-        scene.render_rgb8_device(p, out.data_ptr(), stream=stream.cuda_stream)
-        if sharded:
-            glist = list(gathered.chunk(world)) if rank == 0 else None
-            dist.gather(out, glist, dst=0)
-            if rank == 0:
-                rr.ffi.check(lib.rr_bands_unpack_device(C.byref(p), C.c_void_p(gathered.data_ptr()), shard_bytes,
-                                                        C.c_void_p(frame.data_ptr()), C.c_void_p(stream.cuda_stream)))
-                n += 1
-        return n
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
+    # ---- buffers -------------------------------------------------------------------------------
+    frame_ptr = C.c_void_p()          # the one frame: local on rank 0, NVLink peer mapping elsewhere
+    out = None
+    if sharded:
+        handle = (C.c_uint8 * 64)()
+        if rank == 0:
+            rr.ffi.check(lib.rr_device_alloc(local_rank, frame_bytes, C.byref(frame_ptr)))
+            rr.ffi.check(lib.rr_ipc_export(frame_ptr, handle))
+        box = [bytes(handle)]
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            hb = (C.c_uint8 * 64).from_buffer_copy(box[0])
+            rr.ffi.check(lib.rr_ipc_open(local_rank, hb, C.byref(frame_ptr)))
+        tok = torch.zeros(1, dtype=torch.float32, device=dev)
+        packed = torch.empty(shard_bytes, dtype=torch.uint8, device=dev)
+        gathered = torch.empty(world * shard_bytes, dtype=torch.uint8, device=dev) if rank == 0 else None
+        gframe = torch.empty(frame_bytes, dtype=torch.uint8, device=dev) if rank == 0 else None
+    else:
+        out = torch.empty(frame_bytes, dtype=torch.uint8, device=dev)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)  # evict the previous frame from L2 (not timed)
+    def step_main():
+        """one frame, device resident. returns number of this repo's kernels launched"""
+        if not sharded:
+            scene.render_rgb8_device(p, out.data_ptr(), stream=stream.cuda_stream)
+            return 1
+        rr.ffi.check(lib.rr_render_rgb8_placed_device(scene.handle, C.byref(p), frame_ptr, W * 3, sptr))
+        dist.all_reduce(tok)  # completion fence: rank 0's stream passes it only after every rank's kernel
+        return 1
+
+    def step_gather():
+        scene.render_rgb8_device(p, packed.data_ptr(), stream=stream.cuda_stream)
+        glist = list(gathered.chunk(world)) if rank == 0 else None
+        dist.gather(packed, glist, dst=0)
+        if rank == 0:
+            rr.ffi.check(lib.rr_bands_unpack_device(C.byref(p), C.c_void_p(gathered.data_ptr()), shard_bytes,
+                                                    C.c_void_p(gframe.data_ptr()), sptr))
+            return 2
+        return 1
+
+    def timed(step_fn, steps, sample_clocks):
+        for _ in range(args.warmup):
+            step_fn()
+        barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        launches = 0
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            flush.fill_(i & 0xFF)  # evict the previous frame from L2 (not timed)
+            if dist is not None:
+                dist.barrier()
+            ev[i][0].record(stream)
+            launches += step_fn()
+            ev[i][1].record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop() if sampler else None
+        tot = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
         if dist is not None:
-            dist.barrier()
-        ev[i][0].record(stream)
-        kev[i][0].record(stream)
-        scene.render_rgb8_device(p, out.data_ptr(), stream=stream.cuda_stream)
-        kev[i][1].record(stream)
-        n = 1
-        if sharded:
-            glist = list(gathered.chunk(world)) if rank == 0 else None
-            dist.gather(out, glist, dst=0)
-            if rank == 0:
-                rr.ffi.check(lib.rr_bands_unpack_device(C.byref(p), C.c_void_p(gathered.data_ptr()), shard_bytes,
-                                                        C.c_void_p(frame.data_ptr()), C.c_void_p(stream.cuda_stream)))
-                n += 1
-        ev[i][1].record(stream)
-        launches += n
-    barrier()
-    wall_s = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    kern_ms = [a.elapsed_time(b) for a, b in kev]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    kmean = torch.tensor([sum(kern_ms) / len(kern_ms)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(kmean, op=dist.ReduceOp.MAX)
-    ms_per_step = float(total_ms.item()) / args.steps
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        return float(tot.item()) / steps, launches, clocks, wall
+
+    ms_per_step, launches, clocks, wall_s = timed(step_main, args.steps, True)
     value = rays / (ms_per_step * 1e-3) / 1e6
 
-    # ---- e2e: the reference-facing call, frame delivered to pinned HOST memory -----------------
-    host = C.c_void_p()
-    rr.ffi.check(lib.rr_host_alloc(max(1, my_rows * W * 3), C.byref(host)))
-    for _ in range(3):
-        rr.ffi.check(lib.rr_render_rgb8(scene.handle, C.byref(p), host, 0))
-    barrier()
+    # kernel-only time of this rank's render launch (roofline numerator), same stream, same L2 hygiene
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 30))]
+    kbuf = packed if sharded else out
+    for a, b in kev:
+        flush.fill_(1)
+        a.record(stream)
+        scene.render_rgb8_device(p, kbuf.data_ptr(), stream=stream.cuda_stream)
+        b.record(stream)
+    torch.cuda.synchronize(dev)
+    kt = torch.tensor([sum(a.elapsed_time(b) for a, b in kev) / len(kev)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+    kernel_ms = float(kt.item())
+
+    alt = None
+    frame_check = None
+    if sharded:
+        gms, _, _, _ = timed(step_gather, max(5, args.steps // 2), False)
+        alt = {"method": "nccl gather to rank 0 + rr_bands_unpack_device", "ms_per_step": gms, "value": rays / (gms * 1e-3) / 1e6}
+        # the N-GPU frame must be byte-identical to the 1-GPU frame (and the two assembly methods must agree)
+        step_main()
+        step_gather()
+        barrier()
+        if rank == 0:
+            single = torch.empty(frame_bytes, dtype=torch.uint8, device=dev)
+            scene.render_rgb8_device(ren.frame_params(), single.data_ptr(), stream=stream.cuda_stream)
+            torch.cuda.synchronize(dev)
+            peer = torch.empty(frame_bytes, dtype=torch.uint8, device=dev)
+            whole = ren.frame_params()  # band_count = 1: the unpack kernel degenerates to a row-wise copy
+            rr.ffi.check(lib.rr_bands_unpack_device(C.byref(whole), frame_ptr, frame_bytes, C.c_void_p(peer.data_ptr()), sptr))
+            torch.cuda.synchronize(dev)
+            ok = bool(torch.equal(peer, single)) and bool(torch.equal(gframe, single))
+            frame_check = "identical to the 1-GPU frame" if ok else "MISMATCH"
+        barrier()
+
+    # ---- e2e: the reference-facing call, frame delivered to page-locked HOST memory ------------
     e2e_steps = max(5, min(args.steps, 50))
+    if not sharded:
+        host = C.c_void_p()
+        rr.ffi.check(lib.rr_host_alloc(max(1, frame_bytes), C.byref(host)))
+
+        def e2e_step():
+            rr.ffi.check(lib.rr_render_rgb8(scene.handle, C.byref(p), host, 0))
+    else:
+        shm_path = f"/dev/shm/rr_frame_{os.environ.get('MASTER_PORT', '0')}"
+        if rank == 0:
+            with open(shm_path, "wb") as f:
+                f.truncate(frame_bytes)
+        dist.barrier()
+        shm_f = open(shm_path, "r+b")
+        shm = mmap.mmap(shm_f.fileno(), frame_bytes)
+        host_arr = np.frombuffer(shm, dtype=np.uint8)
+        host = C.c_void_p(host_arr.ctypes.data)
+        rr.ffi.check(lib.rr_host_register(host, frame_bytes))
+
+        def e2e_step():
+            rr.ffi.check(lib.rr_render_rgb8_placed(scene.handle, C.byref(p), host, 0))
+            dist.barrier()
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        rr.ffi.check(lib.rr_render_rgb8(scene.handle, C.byref(p), host, 0))
+        e2e_step()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_s.item()) * 1e3 / e2e_steps
     e2e_value = rays / (e2e_ms * 1e-3) / 1e6
-    lib.rr_host_free(host)
+    e2e_check = None
+    if sharded:
+        if rank == 0:
+            single = np.empty((H, W, 3), dtype=np.uint8)
+            scene.render_rgb8(ren.frame_params(), out=single)
+            e2e_check = "identical to the 1-GPU frame" if np.array_equal(host_arr.reshape(H, W, 3), single) else "MISMATCH"
+        barrier()
+        lib.rr_host_unregister(host)
+        del host_arr
+        shm.close()
+        shm_f.close()
+        dist.barrier()
+        if rank == 0:
+            os.unlink(shm_path)
+    else:
+        lib.rr_host_free(host)
 
     if rank != 0:
+        if sharded:
+            lib.rr_ipc_close(local_rank, frame_ptr)
         scene.close()
         if dist is not None:
             dist.barrier()
@@ -316,9 +406,7 @@ def main():
     sm_max = (peaks or {}).get("sm_max_mhz", 1965.0)
     n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
     derived_unfused = 128 * n_sm * sm_max * 1e6 / 1e12  # 1 flop/lane/clk: FMUL and FADD issue separately (-fmad=false)
-    kernel_ms = float(kmean.item())
-    # one launch renders this rank's share of the frame
-    share = (my_rows / H) if sharded else 1.0
+    share = (my_rows / H) if sharded else 1.0  # one launch renders this rank's share of the frame
     achieved = flops * share / (kernel_ms * 1e-3) / 1e12
     fb_bytes = my_rows * W * 3
     hbm_peak = (peaks or {}).get("hbm_gbs", 6650.0)
@@ -339,6 +427,7 @@ def main():
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         roofline["traffic"] = prof.get(name, {}).get("dram_bytes_per_launch")
+        roofline["traffic_note"] = prof.get(name, {}).get("note")
     except Exception:
         pass
 
@@ -350,8 +439,7 @@ def main():
         threads = os.cpu_count() or 1
         reps = 3 if not march else 1
         if march or WORKLOADS[name][4] == "synthetic":
-            # bounded sample: one interleaved 1/16 of the rows, scaled
-            sp = ren.frame_params(1, 5, 16)
+            sp = ren.frame_params(1, 5, 16)  # bounded sample: one interleaved 1/16 of the rows
             sub = ob.render(ren, params=sp, threads=threads, want_u8=False, want_counts=True)["counts"].rays()
             best = cpu_arm(ob, ren, threads, reps, params=sp)
             cpu = {"value": sub / best / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
@@ -368,20 +456,28 @@ def main():
         "config": {"workload": name, "width": W, "height": H, "mode": "raymarch" if march else "raytrace",
                    "max_reflections": 3, "max_refractions": 10, "rays_per_frame": rays, "ray_classes": counts,
                    "l2": "flushed between timed steps (256 MiB write, untimed)",
-                   "parallelism": f"row-bands{world}x{BAND_ROWS}+nccl-gather" if sharded else "1gpu",
+                   "parallelism": f"row-bands{world}x{BAND_ROWS}, kernel stores rows into rank 0's frame over NVLink (CUDA IPC)"
+                   if sharded else "1gpu",
                    "scene_resident": True},
         "frame_ms": ms_per_step,
         "kernel_ms": kernel_ms,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_frame": e2e_ms, "h2d_bytes_per_step": C.sizeof(rr.ffi.rr_frame_params),
-                "d2h_bytes_per_step": my_rows * W * 3, "api": "rr_render_rgb8 (C ABI) -> pinned host RGB8 frame",
-                "note": "per-rank bands to each rank's host buffer" if sharded else "whole frame"},
+                "d2h_bytes_per_step": my_rows * W * 3,
+                "api": ("rr_render_rgb8_placed (C ABI): each rank's bands -> one shared page-locked host frame, + barrier"
+                        if sharded else "rr_render_rgb8 (C ABI) -> pinned host RGB8 frame"),
+                "check": e2e_check},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "wall_s_timed_region": wall_s,
     }
+    if alt:
+        line["alt"] = alt
+        line["frame_check"] = frame_check
     print(json.dumps(line), flush=True)
+    if sharded:
+        lib.rr_device_free(local_rank, frame_ptr)
     scene.close()
     if dist is not None:
         dist.barrier()

@@ -199,6 +199,28 @@ int rr_render_count(rr_scene *scene, const rr_frame_params *params, uint8_t *out
 int rr_bands_unpack_device(const rr_frame_params *params, const void *d_packed,
                            size_t shard_stride_bytes, void *d_frame, void *cuda_stream);
 
+/* ---- multi-GPU, one process per GPU: shards write into ONE shared frame ----------
+ * The reference gathers finished rows to the caller thread over an mpsc channel (render.rs:846-886).
+ * Here every rank renders its interleaved row bands (params->band_*) and the rows land directly at
+ * their image position in a frame owned by rank 0:
+ *   device frame: rank 0 allocates it with rr_device_alloc and publishes rr_ipc_export's 64-byte handle;
+ *     the other ranks map it with rr_ipc_open (NVLink peer memory) and pass the mapped pointer to
+ *     rr_render_rgb8_placed_device — the render kernel's own stores cross NVLink, there is no gather
+ *     or un-interleave pass. Completion is ordered by the caller (stream sync + a barrier).
+ *   host frame: a buffer shared between the processes (e.g. POSIX shared memory), page-locked in each
+ *     with rr_host_register; rr_render_rgb8_placed copies this rank's bands over its own PCIe link. */
+int rr_render_rgb8_placed_device(rr_scene *scene, const rr_frame_params *params, void *d_frame,
+                                 size_t row_stride, void *cuda_stream);
+int rr_render_rgb8_placed(rr_scene *scene, const rr_frame_params *params, uint8_t *host_frame,
+                          size_t row_stride);
+int rr_device_alloc(int device, size_t bytes, void **d_ptr);
+int rr_device_free(int device, void *d_ptr);
+int rr_ipc_export(void *d_ptr, uint8_t handle[64]);
+int rr_ipc_open(int device, const uint8_t handle[64], void **d_ptr);
+int rr_ipc_close(int device, void *d_ptr);
+int rr_host_register(void *ptr, size_t bytes);
+int rr_host_unregister(void *ptr);
+
 /* Pinned host memory for frame buffers (full-speed D2H). Plain malloc'd buffers also work. */
 int rr_host_alloc(size_t bytes, void **out);
 int rr_host_free(void *ptr);

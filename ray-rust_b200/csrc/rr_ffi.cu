@@ -117,7 +117,7 @@ rr::FrameParams to_dev(const rr_frame_params *p) {
 
 int launch(rr_scene *s, const rr::FrameParams &P, void *d_out, size_t row_stride, bool f32, rr::Counters *d_cnt,
            cudaStream_t st) {
-    cudaError_t e = P.use_raymarching ? rr::launch_march(s->G, P, d_out, row_stride, f32, d_cnt, s->d_work, st, s->li)
+    cudaError_t e = P.use_raymarching ? rr::launch_march(s->G, s->H, P, d_out, row_stride, f32, d_cnt, s->d_work, st, s->li)
                                       : rr::launch_trace(s->G, s->H, P, d_out, row_stride, f32, d_cnt, st, s->li, s->culling);
     if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
     return RR_OK;
@@ -331,7 +331,23 @@ int rr_scene_create(const rr_scene_desc *desc, int device, rr_scene **out) {
         }
     }
 
-    for (int k = 0; k < rr::RR_HEAD_SPHERES && k < (int)sph.size(); ++k) { s->H.sph[k] = sph[k]; s->H.sph_oi[k] = sph_oi[k]; }
+    for (int k = 0; k < rr::RR_HEAD_SPHERES && k < (int)sph.size(); ++k) { s->H.sph[k] = sph[k]; s->H.sph_oi[k] = sph_oi[k]; s->H.sph_m[k] = sph_m[k]; s->H.sph_glow[k] = sph_glow[k]; }
+    {   // glowing objects for the march kernel's separate glow pass
+        int ng = 0;
+        for (uint32_t i = 0; i < desc->n_objects && ng >= 0; ++i) {
+            const rr_object &o = desc->objects[i];
+            const rr_material &m = desc->materials[o.material];
+            if (m.glow_dist == 0.0f) continue;
+            if (ng == rr::RR_HEAD_GLOW) { ng = -1; break; }
+            s->H.glow_a[ng] = make_float4(o.org[0], o.org[1], o.org[2], o.kind == RR_SPHERE ? o.r : 0.0f);
+            s->H.glow_b[ng] = make_float4(o.face_normal[0], o.face_normal[1], o.face_normal[2], 0.0f);
+            s->H.glow_k[ng] = m.glow_dist;
+            s->H.glow_kind[ng] = o.kind == RR_SPHERE ? 0 : 1;
+            s->H.glow_oi[ng] = (int)i;
+            ++ng;
+        }
+        s->H.n_glow_head = ng;
+    }
     for (int k = 0; k < rr::RR_HEAD_FLOORS && k < (int)flo_o.size(); ++k) {
         s->H.flo_o[k] = flo_o[k]; s->H.flo_n[k] = flo_n[k]; s->H.flo_oi[k] = flo_oi[k];
     }
@@ -501,6 +517,119 @@ int rr_bands_unpack_device(const rr_frame_params *params, const void *d_packed, 
     cudaError_t e = rr::launch_bands_unpack(P, d_packed, shard_stride_bytes, d_frame, reinterpret_cast<cudaStream_t>(cuda_stream));
     if (e != cudaSuccess) return fail_cuda(e, "bands_unpack");
     if (!cuda_stream) CU(cudaStreamSynchronize(nullptr));
+    return RR_OK;
+}
+
+// ---- multi-GPU: placed output into one shared frame (device: peer memory via CUDA IPC; host: registered memory) ----
+int rr_render_rgb8_placed_device(rr_scene *s, const rr_frame_params *params, void *d_frame, size_t row_stride, void *cuda_stream) {
+    if (!s || !d_frame) return fail(RR_ERR_BAD_ARG, "scene/d_frame is null");
+    int rc = check_params(params);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->device));
+    rr::FrameParams P = to_dev(params);
+    P.placed = 1;
+    if (row_stride == 0) row_stride = (size_t)P.xres * 3;
+    if (row_stride < (size_t)P.xres * 3) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
+    if (cuda_stream) return launch(s, P, d_frame, row_stride, false, nullptr, reinterpret_cast<cudaStream_t>(cuda_stream));
+    CU(cudaEventRecord(s->ev0, s->stream));
+    if ((rc = launch(s, P, d_frame, row_stride, false, nullptr, s->stream))) return rc;
+    CU(cudaEventRecord(s->ev1, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+    s->timed = true;
+    return RR_OK;
+}
+
+// This shard's bands rendered packed on the device, then copied straight to their rows of a full
+// frame in host memory (each GPU over its own PCIe link when several processes share the frame).
+int rr_render_rgb8_placed(rr_scene *s, const rr_frame_params *params, uint8_t *host_frame, size_t row_stride) {
+    if (!s || !host_frame) return fail(RR_ERR_BAD_ARG, "scene/host_frame is null");
+    int rc = check_params(params);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->device));
+    rr::FrameParams P = to_dev(params);
+    const size_t packed = (size_t)P.xres * 3;
+    if (row_stride == 0) row_stride = packed;
+    if (row_stride < packed) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
+    const int rows = P.local_rows;
+    if (rows == 0 || P.xres == 0) return RR_OK;
+    if ((rc = ensure_out(s, packed * rows))) return rc;
+    CU(cudaEventRecord(s->ev0, s->stream));
+    if ((rc = launch(s, P, s->d_out, packed, false, nullptr, s->stream))) return rc;
+    CU(cudaEventRecord(s->ev1, s->stream));
+    const int B = P.band_rows, n = P.band_count, k = P.band_index;
+    if (n <= 1) {
+        CU(cudaMemcpy2DAsync(host_frame, row_stride, s->d_out, packed, packed, (size_t)rows, cudaMemcpyDeviceToHost, s->stream));
+    } else if (row_stride == packed) {
+        // full bands: one strided copy (a band is B contiguous rows; bands of this shard are n*B rows apart)
+        const int full = rows / B, tail = rows - full * B;
+        const size_t band_bytes = (size_t)B * packed;
+        if (full > 0)
+            CU(cudaMemcpy2DAsync(host_frame + (size_t)k * band_bytes, (size_t)n * band_bytes, s->d_out, band_bytes, band_bytes,
+                                 (size_t)full, cudaMemcpyDeviceToHost, s->stream));
+        if (tail > 0)
+            CU(cudaMemcpyAsync(host_frame + ((size_t)full * n + k) * band_bytes, reinterpret_cast<uint8_t *>(s->d_out) + (size_t)full * band_bytes,
+                               (size_t)tail * packed, cudaMemcpyDeviceToHost, s->stream));
+    } else {
+        for (int r0 = 0; r0 < rows; r0 += B) {  // padded rows: one 2D copy per band
+            const int nr = rows - r0 < B ? rows - r0 : B;
+            const size_t iy = ((size_t)(r0 / B) * n + k) * B;
+            CU(cudaMemcpy2DAsync(host_frame + iy * row_stride, row_stride, reinterpret_cast<uint8_t *>(s->d_out) + (size_t)r0 * packed, packed,
+                                 packed, (size_t)nr, cudaMemcpyDeviceToHost, s->stream));
+        }
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+    s->timed = true;
+    return RR_OK;
+}
+
+int rr_device_alloc(int device, size_t bytes, void **d_ptr) {
+    if (!d_ptr) return fail(RR_ERR_BAD_ARG, "d_ptr is null");
+    *d_ptr = nullptr;
+    CU(cudaSetDevice(device));
+    CU(cudaMalloc(d_ptr, bytes ? bytes : 1));
+    return RR_OK;
+}
+int rr_device_free(int device, void *d_ptr) {
+    if (!d_ptr) return RR_OK;
+    CU(cudaSetDevice(device));
+    CU(cudaFree(d_ptr));
+    return RR_OK;
+}
+int rr_ipc_export(void *d_ptr, uint8_t handle[64]) {
+    if (!d_ptr || !handle) return fail(RR_ERR_BAD_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, d_ptr));
+    std::memcpy(handle, &h, 64);
+    return RR_OK;
+}
+int rr_ipc_open(int device, const uint8_t handle[64], void **d_ptr) {
+    if (!d_ptr || !handle) return fail(RR_ERR_BAD_ARG, "null argument");
+    *d_ptr = nullptr;
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RR_OK;
+}
+int rr_ipc_close(int device, void *d_ptr) {
+    if (!d_ptr) return RR_OK;
+    CU(cudaSetDevice(device));
+    CU(cudaIpcCloseMemHandle(d_ptr));
+    return RR_OK;
+}
+int rr_host_register(void *ptr, size_t bytes) {
+    if (!ptr) return fail(RR_ERR_BAD_ARG, "ptr is null");
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return RR_OK;
+}
+int rr_host_unregister(void *ptr) {
+    if (!ptr) return RR_OK;
+    CU(cudaHostUnregister(ptr));
     return RR_OK;
 }
 

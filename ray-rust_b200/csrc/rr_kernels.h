@@ -19,7 +19,7 @@ struct LaunchInfo {
 cudaError_t launch_trace(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
                          Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh);
 // Ray-march mode (same contract). d_work: one unsigned int work counter (zeroed by the launcher).
-cudaError_t launch_march(const DevScene &G, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
+cudaError_t launch_march(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
                          Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li);
 // Row-band un-interleave (multi-GPU gather epilogue).
 cudaError_t launch_bands_unpack(const FrameParams &P, const void *d_packed, size_t shard_stride, void *d_frame,

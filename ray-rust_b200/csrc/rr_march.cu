@@ -11,39 +11,43 @@ namespace rr {
 
 constexpr int MARCH_THREADS = 128;
 
+template <typename T>
+__device__ __forceinline__ void copy_tail(T *dst, const T *src, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+// Only the list tails (objects beyond the SceneHead) are staged; small scenes stage nothing.
 __device__ __forceinline__ MarchView stage_march(const DevScene &G, float4 *smem, bool stage) {
     MarchView S;
     S.n_spheres = G.n_spheres;
     S.n_floors = G.n_floors;
-    if (!stage) {
-        S.sph = G.sph_m; S.sph_glow = G.sph_glow; S.sph_oi = G.sph_oi; S.flo_o = G.flo_o; S.flo_n = G.flo_n; S.flo_oi = G.flo_oi;
-        return S;
-    }
-    float4 *sph = smem;
-    float4 *flo_o = sph + G.n_spheres;
-    float4 *flo_n = flo_o + G.n_floors;
-    float *sph_glow = reinterpret_cast<float *>(flo_n + G.n_floors);
-    int *sph_oi = reinterpret_cast<int *>(sph_glow + G.n_spheres);
-    int *flo_oi = sph_oi + G.n_spheres;
-    for (int i = threadIdx.x; i < G.n_spheres; i += blockDim.x) {
-        sph[i] = G.sph_m[i];
-        sph_glow[i] = G.sph_glow[i];
-        sph_oi[i] = G.sph_oi[i];
-    }
-    for (int i = threadIdx.x; i < G.n_floors; i += blockDim.x) {
-        flo_o[i] = G.flo_o[i];
-        flo_n[i] = G.flo_n[i];
-        flo_oi[i] = G.flo_oi[i];
-    }
+    S.sph = G.sph_m; S.sph_glow = G.sph_glow; S.sph_oi = G.sph_oi; S.flo_o = G.flo_o; S.flo_n = G.flo_n; S.flo_oi = G.flo_oi;
+    if (!stage) return S;
+    const int ts = max(G.n_spheres - RR_HEAD_SPHERES, 0), tf = max(G.n_floors - RR_HEAD_FLOORS, 0);
+    if (ts + tf == 0) return S;
+    float4 *p = smem;
+    float4 *sph = p; p += ts;
+    float4 *flo_o = p; p += tf;
+    float4 *flo_n = p; p += tf;
+    float *sph_glow = reinterpret_cast<float *>(p);
+    int *sph_oi = reinterpret_cast<int *>(sph_glow + ts);
+    int *flo_oi = sph_oi + ts;
+    copy_tail(sph, G.sph_m + RR_HEAD_SPHERES, ts);
+    copy_tail(sph_glow, G.sph_glow + RR_HEAD_SPHERES, ts);
+    copy_tail(sph_oi, G.sph_oi + RR_HEAD_SPHERES, ts);
+    copy_tail(flo_o, G.flo_o + RR_HEAD_FLOORS, tf);
+    copy_tail(flo_n, G.flo_n + RR_HEAD_FLOORS, tf);
+    copy_tail(flo_oi, G.flo_oi + RR_HEAD_FLOORS, tf);
     __syncthreads();
-    S.sph = sph; S.sph_glow = sph_glow; S.sph_oi = sph_oi; S.flo_o = flo_o; S.flo_n = flo_n; S.flo_oi = flo_oi;
+    S.sph = sph - RR_HEAD_SPHERES; S.sph_glow = sph_glow - RR_HEAD_SPHERES; S.sph_oi = sph_oi - RR_HEAD_SPHERES;
+    S.flo_o = flo_o - RR_HEAD_FLOORS; S.flo_n = flo_n - RR_HEAD_FLOORS; S.flo_oi = flo_oi - RR_HEAD_FLOORS;
     return S;
 }
 
-template <bool COUNT, bool F32OUT, bool STAGE, bool GLOW>
+template <bool COUNT, bool F32OUT, bool STAGE, int GLOW>
 __global__ void __launch_bounds__(MARCH_THREADS)
-march_kernel(const DevScene G, const FrameParams P, void *__restrict__ out, size_t row_stride, Counters *gcnt,
-             unsigned *work, int fast_store) {
+march_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHead H, const __grid_constant__ FrameParams P,
+             void *__restrict__ out, size_t row_stride, Counters *gcnt, unsigned *work, int fast_store) {
     extern __shared__ float4 rr_smem[];
     const MarchView S = stage_march(G, rr_smem, STAGE);
 
@@ -64,28 +68,30 @@ march_kernel(const DevScene G, const FrameParams P, void *__restrict__ out, size
         const int ix = x0 + col, ly = ly0 + row;
         const bool valid = ix < W && ly < rows;
         V3 c = mk(0.0f, 0.0f, 0.0f);
-        if (valid) c = march_pixel<COUNT, GLOW>(G, S, P, ix, local_to_image_row(P, ly), cnt);
+        if (valid) c = march_pixel<COUNT, GLOW>(G, H, S, P, ix, local_to_image_row(P, ly), cnt);
         if (F32OUT) {
             if (valid) {
-                float *o = reinterpret_cast<float *>(out) + ((size_t)ly * W + ix) * 3;
+                float *o = reinterpret_cast<float *>(out) + ((size_t)(P.placed ? local_to_image_row(P, ly) : ly) * W + ix) * 3;
                 o[0] = c.x; o[1] = c.y; o[2] = c.z;
             }
         } else {
             const unsigned rgb = quantize(c.x) | (quantize(c.y) << 8) | (quantize(c.z) << 16);
-            store_tile_rgb8(reinterpret_cast<uint8_t *>(out), row_stride, x0, ly0, W, rows, rgb, fast_store != 0);
+            store_tile_rgb8(reinterpret_cast<uint8_t *>(out), row_stride, x0, ly0, W, rows, rgb, fast_store != 0,
+                            P.placed ? local_to_image_row(P, ly) : ly);
         }
     }
     if (COUNT) flush_counters(cnt, gcnt);
 }
 
 static size_t march_smem_bytes(const DevScene &G) {
-    return (size_t)G.n_spheres * (sizeof(float4) + sizeof(float) + sizeof(int)) +
-           (size_t)G.n_floors * (2 * sizeof(float4) + sizeof(int)) + 16;
+    const size_t ts = G.n_spheres > RR_HEAD_SPHERES ? G.n_spheres - RR_HEAD_SPHERES : 0;
+    const size_t tf = G.n_floors > RR_HEAD_FLOORS ? G.n_floors - RR_HEAD_FLOORS : 0;
+    return ts * (sizeof(float4) + sizeof(float) + sizeof(int)) + tf * (2 * sizeof(float4) + sizeof(int)) + 16;
 }
 
-template <bool COUNT, bool F32OUT, bool STAGE, bool GLOW>
-static cudaError_t launch_one(const DevScene &G, const FrameParams &P, void *d_out, size_t row_stride, Counters *d_cnt,
-                              unsigned *d_work, cudaStream_t stream, const LaunchInfo &li, size_t smem) {
+template <bool COUNT, bool F32OUT, bool STAGE, int GLOW>
+static cudaError_t launch_one(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
+                              Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li, size_t smem) {
     auto kern = march_kernel<COUNT, F32OUT, STAGE, GLOW>;
     cudaError_t e;
     if (smem > 48 * 1024) {
@@ -96,38 +102,44 @@ static cudaError_t launch_one(const DevScene &G, const FrameParams &P, void *d_o
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MARCH_THREADS, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    const int tiles = ((P.xres + 7) / 8) * ((P.local_rows + 3) / 4);
-    const int need = (tiles + (MARCH_THREADS / 32) - 1) / (MARCH_THREADS / 32);
-    int grid = li.sm_count * per_sm;
+    const long long tiles = (long long)((P.xres + 7) / 8) * ((P.local_rows + 3) / 4);
+    const long long need = (tiles + (MARCH_THREADS / 32) - 1) / (MARCH_THREADS / 32);
+    long long grid = (long long)li.sm_count * per_sm;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     e = cudaMemsetAsync(d_work, 0, sizeof(unsigned), stream);
     if (e != cudaSuccess) return e;
     const int fast = (!F32OUT && (P.xres % 8 == 0) && (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0)) ? 1 : 0;
-    kern<<<grid, MARCH_THREADS, smem, stream>>>(G, P, d_out, row_stride, d_cnt, d_work, fast);
+    kern<<<(unsigned)grid, MARCH_THREADS, smem, stream>>>(G, H, P, d_out, row_stride, d_cnt, d_work, fast);
     return cudaGetLastError();
 }
 
 template <bool COUNT, bool F32OUT>
-static cudaError_t launch_two(const DevScene &G, const FrameParams &P, void *d_out, size_t row_stride, Counters *d_cnt,
-                              unsigned *d_work, cudaStream_t stream, const LaunchInfo &li) {
+static cudaError_t launch_two(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
+                              Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li) {
     size_t smem = march_smem_bytes(G);
     const bool stage = smem <= li.smem_optin / 2;
     if (!stage) smem = 0;
-    const bool glow = P.glow_enabled && G.n_glow > 0;
-    if (stage) return glow ? launch_one<COUNT, F32OUT, true, true>(G, P, d_out, row_stride, d_cnt, d_work, stream, li, smem)
-                           : launch_one<COUNT, F32OUT, true, false>(G, P, d_out, row_stride, d_cnt, d_work, stream, li, smem);
-    return glow ? launch_one<COUNT, F32OUT, false, true>(G, P, d_out, row_stride, d_cnt, d_work, stream, li, smem)
-                : launch_one<COUNT, F32OUT, false, false>(G, P, d_out, row_stride, d_cnt, d_work, stream, li, smem);
+    // glow tracking: 0 = nothing reads it, 1 = separate pass over the <= RR_HEAD_GLOW glowing objects,
+    // 2 = inline in the scan (many glowing objects)
+    const int glow = !(P.glow_enabled && G.n_glow > 0) ? 0 : (H.n_glow_head >= 0 ? 1 : 2);
+    if (stage) {
+        if (glow == 0) return launch_one<COUNT, F32OUT, true, 0>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, smem);
+        if (glow == 1) return launch_one<COUNT, F32OUT, true, 1>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, smem);
+        return launch_one<COUNT, F32OUT, true, 2>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, smem);
+    }
+    if (glow == 0) return launch_one<COUNT, F32OUT, false, 0>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, smem);
+    if (glow == 1) return launch_one<COUNT, F32OUT, false, 1>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, smem);
+    return launch_one<COUNT, F32OUT, false, 2>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, smem);
 }
 
-cudaError_t launch_march(const DevScene &G, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
-                         Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li) {
+cudaError_t launch_march(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
+                         bool f32_out, Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li) {
     if (P.xres <= 0 || P.local_rows <= 0) return cudaSuccess;
-    if (d_cnt) return f32_out ? launch_two<true, true>(G, P, d_out, row_stride, d_cnt, d_work, stream, li)
-                              : launch_two<true, false>(G, P, d_out, row_stride, d_cnt, d_work, stream, li);
-    return f32_out ? launch_two<false, true>(G, P, d_out, row_stride, d_cnt, d_work, stream, li)
-                   : launch_two<false, false>(G, P, d_out, row_stride, d_cnt, d_work, stream, li);
+    if (d_cnt) return f32_out ? launch_two<true, true>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li)
+                              : launch_two<true, false>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li);
+    return f32_out ? launch_two<false, true>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li)
+                   : launch_two<false, false>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li);
 }
 
 }  // namespace rr

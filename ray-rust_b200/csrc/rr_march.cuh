@@ -1,15 +1,25 @@
 // rr_march.cuh — ray-march mode of the per-pixel path (render.rs:1226-1411) as device functions.
 //
 // raymarch_single()'s sphere-tracing loop is the hot loop (up to 10 001 dependent iterations, each
-// an O(N) distance scan). The scan runs over the same shared-memory SoA lists as the trace kernel;
-// the glow distance (render.rs:1244-1247) is only tracked when --gloweffect is set and the scene
-// has a glowing material, because nothing else reads it.
+// an O(N) distance scan). Design:
+//   * the scan runs over the SceneHead (first floors/spheres as constant-bank operands, fully
+//     unrolled) and then over shared-memory tails, like the trace kernel;
+//   * EXACT sqrt skipping: distance_estimate only needs the minimum of max(|c - p| - r, 0). A sphere
+//     whose squared centre distance exceeds ((best + r) * (1 + 2^-19))^2 provably has an f32 distance
+//     strictly above the running minimum (proof in sphere_dist), so its sqrt/sub/max/compare are
+//     skipped without changing a bit of the result. Spheres with a glowing material are always
+//     evaluated when glow is tracked, because the glow minimum needs their distance;
+//   * one march call site: a per-thread state machine alternates "trace march" and "shadow march",
+//     so the loop body exists once; the glow distance (render.rs:1244-1247) is tracked only for trace
+//     marches and only when --gloweffect is set and a glowing material exists (nothing else reads it);
+//   * the march-mode miss quirk (render.rs:1385-1393) is executed as "march once, replay the
+//     accumulation" (the repeated marches are bit-identical).
 #pragma once
 #include "rr_device.cuh"
 
 namespace rr {
 
-struct MarchView {
+struct MarchView {  // list tails (shared memory when staged), indexed with the global list index
     const float4 *sph;     // (cx, cy, cz, r)
     const float *sph_glow; // glow_dist per sphere
     const int *sph_oi;
@@ -28,41 +38,87 @@ struct MarchResult {  // render.rs:1257-1264
     float min_dist;
 };
 
-// distance_estimate, render.rs:1226-1251 (+ distance(): :473-475 sphere, :571-573 floor).
-// Lowest original index wins ties, as the reference's in-order strict `<` scan does.
-template <bool GLOW>
-__device__ __forceinline__ void distance_estimate(const MarchView &S, const V3 &vi, int ig, float &closest, int &idx_out,
-                                                  float &glowing) {
+// RenderFloor::distance, render.rs:571-573, folded into the running minimum of render.rs:1238-1247
+template <int GLOW>
+__device__ __forceinline__ void floor_dist(const float4 &o, const float4 &n, int oi, const V3 &vi, int ig, bool track,
+                                           float &best, int &idx, float &gl) {
+    if (oi == ig) return;
+    const float dist = fmaxf(dot(vi - mk(o.x, o.y, o.z), mk(n.x, n.y, n.z)), 0.0f);
+    if (dist < best) {  // floors are scanned first and in index order: strict <
+        best = dist;
+        idx = oi;
+    }
+    if (GLOW == 2 && track) {
+        const float g = dist * o.w;
+        if (0.0f < g && g < gl) gl = g;
+    }
+}
+
+// RenderSphere::distance, render.rs:473-475: max(len(org - vi) - r, 0).
+//
+// Skip rule. Let T = fl(best + r) with r >= 0 and sq = the f32 squared length. If
+// sq > fl(fl(T*T) * 1.000004) then, with u = 2^-24: sq > (best+r)^2 (1 + 3.6e-6), so the correctly
+// rounded sqrt is >= (best+r)(1 + 1.7e-6), and fl(sqrt - r) >= (best + 1.7e-6 (best+r)) (1-u) > best.
+// Hence dist > best strictly: the sphere can neither lower the minimum nor tie with it, and
+// skipping it leaves (best, idx) exactly as the reference's scan would. best = inf never skips.
+template <int GLOW>
+__device__ __forceinline__ void sphere_dist(const float4 &c, float glow, int oi, const V3 &vi, int ig, bool track,
+                                            float &best, int &idx, float &gl) {
+    if (oi == ig) return;
+    const V3 d = mk(c.x, c.y, c.z) - vi;
+    const float sq = d.x * d.x + d.y * d.y + d.z * d.z;
+    const bool glows = GLOW == 2 && track && glow != 0.0f;
+    if (!glows && c.w >= 0.0f) {
+        const float T = best + c.w;
+        if (sq > T * T * 1.000004f) return;
+    }
+    const float dist = fmaxf(sqrtf(sq) - c.w, 0.0f);
+    if (dist < best || (dist == best && oi < idx && dist < RR_INF)) {  // lowest original index wins ties
+        best = dist;
+        idx = oi;
+    }
+    if (glows) {
+        const float g = dist * glow;
+        if (0.0f < g && g < gl) gl = g;
+    }
+}
+
+// distance_estimate, render.rs:1226-1251
+template <int GLOW>
+__device__ __forceinline__ void distance_estimate(const SceneHead &H, const MarchView &S, const V3 &vi, int ig, bool track,
+                                                  float &closest, int &idx_out, float &glowing) {
     float best = RR_INF, gl = RR_INF;
     int idx = 0;
-    for (int f = 0; f < S.n_floors; ++f) {
-        const int oi = S.flo_oi[f];
-        if (oi == ig) continue;
-        const float4 o = S.flo_o[f];
-        const float4 n = S.flo_n[f];
-        const float dist = fmaxf(dot(vi - mk(o.x, o.y, o.z), mk(n.x, n.y, n.z)), 0.0f);
-        if (dist < best) {
-            best = dist;
-            idx = oi;
-        }
-        if (GLOW) {
-            const float g = dist * o.w;
-            if (0.0f < g && g < gl) gl = g;
-        }
-    }
-    for (int s = 0; s < S.n_spheres; ++s) {
-        const float4 c = S.sph[s];
-        const V3 d = mk(c.x, c.y, c.z) - vi;
-        const float dist = fmaxf(sqrtf(d.x * d.x + d.y * d.y + d.z * d.z) - c.w, 0.0f);
-        const int oi = S.sph_oi[s];
-        if (oi == ig) continue;
-        if (dist < best || (dist == best && oi < idx && dist < RR_INF)) {
-            best = dist;
-            idx = oi;
-        }
-        if (GLOW) {
-            const float g = dist * S.sph_glow[s];
-            if (0.0f < g && g < gl) gl = g;
+#pragma unroll
+    for (int f = 0; f < RR_HEAD_FLOORS; ++f)
+        if (f < S.n_floors) floor_dist<GLOW>(H.flo_o[f], H.flo_n[f], H.flo_oi[f], vi, ig, track, best, idx, gl);
+    for (int f = RR_HEAD_FLOORS; f < S.n_floors; ++f)
+        floor_dist<GLOW>(S.flo_o[f], S.flo_n[f], S.flo_oi[f], vi, ig, track, best, idx, gl);
+#pragma unroll
+    for (int s = 0; s < RR_HEAD_SPHERES; ++s)
+        if (s < S.n_spheres) sphere_dist<GLOW>(H.sph_m[s], H.sph_glow[s], H.sph_oi[s], vi, ig, track, best, idx, gl);
+#pragma unroll 2
+    for (int s = RR_HEAD_SPHERES; s < S.n_spheres; ++s)
+        sphere_dist<GLOW>(S.sph[s], GLOW == 2 ? S.sph_glow[s] : 0.0f, S.sph_oi[s], vi, ig, track, best, idx, gl);
+    if (GLOW == 1 && track) {
+        // glow pass (render.rs:1244-1247) over the few glowing objects only; their distance is formed
+        // with the same operations as in the scan, so the bits are the same whether or not the scan
+        // above skipped the object's sqrt.
+#pragma unroll
+        for (int g = 0; g < RR_HEAD_GLOW; ++g) {
+            if (g < H.n_glow_head && H.glow_oi[g] != ig) {
+                const float4 a = H.glow_a[g];
+                float dist;
+                if (H.glow_kind[g] == 0) {
+                    const V3 d = mk(a.x, a.y, a.z) - vi;
+                    dist = fmaxf(sqrtf(d.x * d.x + d.y * d.y + d.z * d.z) - a.w, 0.0f);
+                } else {
+                    const float4 nn = H.glow_b[g];
+                    dist = fmaxf(dot(vi - mk(a.x, a.y, a.z), mk(nn.x, nn.y, nn.z)), 0.0f);
+                }
+                const float gv = dist * H.glow_k[g];
+                if (0.0f < gv && gv < gl) gl = gv;
+            }
         }
     }
     closest = best;
@@ -71,8 +127,9 @@ __device__ __forceinline__ void distance_estimate(const MarchView &S, const V3 &
 }
 
 // raymarch_single, render.rs:1266-1297
-template <bool GLOW>
-__device__ __forceinline__ MarchResult raymarch_single(const MarchView &S, const V3 &init_pos, const V3 &eye, int ig) {
+template <int GLOW>
+__device__ __forceinline__ MarchResult raymarch_single(const SceneHead &H, const MarchView &S, const V3 &init_pos,
+                                                       const V3 &eye, int ig, bool track) {
     int iter = 0;
     float travel = 0.0f;
     V3 pos = init_pos;
@@ -80,7 +137,7 @@ __device__ __forceinline__ MarchResult raymarch_single(const MarchView &S, const
     for (;;) {
         float dist, gl;
         int idx;
-        distance_estimate<GLOW>(S, pos, ig, dist, idx, gl);
+        distance_estimate<GLOW>(H, S, pos, ig, track, dist, idx, gl);
         pos = (eye * dist) + pos;
         travel += dist;
         iter += 1;
@@ -99,7 +156,6 @@ struct MarchFrame {  // a suspended raymarch() frame waiting for its refraction 
     float mmd;  // min_min_dist of the suspended frame
     int ig;
     int lev;
-    unsigned flags;
     int cont;
 };
 
@@ -112,81 +168,111 @@ __device__ __forceinline__ V3 apply_glow(const FrameParams &P, const V3 &c, floa
     return mk(factor * c.x, factor * c.y, factor * c.z);
 }
 
-template <bool COUNT, bool GLOW>
-__device__ __forceinline__ V3 march_pixel(const DevScene &G, const MarchView &S, const FrameParams &P, int ix, int iy,
-                                          Counters &cnt) {
+template <bool COUNT, int GLOW>
+__device__ __forceinline__ V3 march_pixel(const DevScene &G, const SceneHead &H, const MarchView &S, const FrameParams &P,
+                                          int ix, int iy, Counters &cnt) {
     const V3 light = mk(P.light[0], P.light[1], P.light[2]);
     V3 pos = mk(P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]);
     V3 eye = primary_ray(P, ix, iy);
     int lev = 0, ig = -1, depth = 0;
-    unsigned flags = 0;
     V3 ret = mk(0.0f, 0.0f, 0.0f), fcs = mk(1.0f, 1.0f, 1.0f);
     float mmd = RR_INF;
     MarchFrame stack[RR_MARCH_MAX_STACK];
     int ray_class = 0;
+    bool shadow_phase = false;
+    int hidx = 0;
+    V3 pt = pos, n = pos;
+    float diffuse_intensity = 0.0f, reflection_intensity = 0.0f;
     if (COUNT) cnt.pixels++;
 
     for (;;) {
-        lev += 1;  // render.rs:1317
-        const MarchResult r = raymarch_single<GLOW>(S, pos, eye, ig);
+        // ---- the one march: the frame's trace ray or the shadow ray of a hit ----
+        V3 ro, rd;
+        int rig;
+        if (!shadow_phase) {
+            lev += 1;  // render.rs:1317
+            ro = pos; rd = eye; rig = ig;
+        } else {
+            ro = pt + (light * F32_EPSILON);  // render.rs:1034
+            rd = light; rig = hidx;
+        }
+        const MarchResult r = raymarch_single<GLOW>(H, S, ro, rd, rig, !shadow_phase);
         if (COUNT) {
-            if (ray_class == 0) cnt.primary++;
+            if (shadow_phase) {
+                cnt.shadow++;
+                if (__ldg(&G.obj_b[hidx]).x == 0) cnt.sphere_hits++;
+            } else if (ray_class == 0) cnt.primary++;
             else if (ray_class == 1) cnt.refract++;
             else cnt.reflect++;
             cnt.march_steps += (unsigned long long)r.iter;
-            cnt.object_tests += (unsigned long long)r.iter * (unsigned long long)(G.n_objects - (ig >= 0 ? 1 : 0));
-            cnt.sphere_tests += (unsigned long long)r.iter * (unsigned long long)spheres_tested(G, ig);
+            cnt.object_tests += (unsigned long long)r.iter * (unsigned long long)(G.n_objects - (rig >= 0 ? 1 : 0));
+            cnt.sphere_tests += (unsigned long long)r.iter * (unsigned long long)spheres_tested(G, rig);
         }
-        if (r.min_dist < mmd) mmd = r.min_dist;
-        bool frame_done;
-        if (r.final_dist < RAYMARCH_EPS) {
-            const int idx = r.idx;
-            const V3 pt = r.pos;
+
+        bool frame_done = false;
+        if (!shadow_phase) {
+            if (GLOW && r.min_dist < mmd) mmd = r.min_dist;
+            if (r.final_dist < RAYMARCH_EPS) {
+                // hit: first half of shading(), render.rs:1020-1046, then march the shadow ray
+                hidx = r.idx;
+                pt = r.pos;
+                const float4 oa = __ldg(&G.obj_a[hidx]);
+                const int4 ob = __ldg(&G.obj_b[hidx]);
+                if (ob.x == 0) {
+                    n = normalized(pt - mk(oa.x, oa.y, oa.z));
+                } else {
+                    const float4 n4 = __ldg(&G.obj_n[hidx]);
+                    n = mk(n4.x, n4.y, n4.z);
+                }
+                const float light_incidence = dot(light, n);
+                const float ln2 = 2.0f * light_incidence;
+                const V3 rr_light = (n * ln2) - light;
+                const int pn = G.mat[ob.z].pn;
+                diffuse_intensity = fmaxf(light_incidence, 0.0f);
+                reflection_intensity = 0.0f;
+                if (pn != 0) {
+                    const float ri = -dot(rr_light, eye);
+                    if (ri > 0.0f) reflection_intensity = rs_powi(ri, pn);
+                }
+                shadow_phase = true;
+                continue;
+            }
+            // Miss (render.rs:1385-1393): bg is added and, because pos/eye/ig are unchanged, the very
+            // same march repeats until lev reaches MAX_REFLECTIONS. The repeats are bit-identical, so
+            // the march result is reused and only the accumulation is replayed (appendix A Q15).
+            const V3 bg = bgcolor(P, eye);
+            for (;;) {
+                if (COUNT) cnt.bg_evals++;
+                ret = mk(ret.x + bg.x * fcs.x, ret.y + bg.y * fcs.y, ret.z + bg.z * fcs.z);
+                if (MAX_REFLECTIONS_CONST <= lev) break;
+                lev += 1;
+                if (COUNT) {  // the reference re-marches here
+                    cnt.reflect++;
+                    cnt.march_steps += (unsigned long long)r.iter;
+                    cnt.object_tests += (unsigned long long)r.iter * (unsigned long long)(G.n_objects - (ig >= 0 ? 1 : 0));
+                    cnt.sphere_tests += (unsigned long long)r.iter * (unsigned long long)spheres_tested(G, ig);
+                }
+            }
+            frame_done = true;
+        } else {
+            // ---- second half of shading(), march-mode shadow rule render.rs:1052-1067 ----
+            shadow_phase = false;
+            const int idx = hidx;
             const float4 oa = __ldg(&G.obj_a[idx]);
             const int4 ob = __ldg(&G.obj_b[idx]);
-            V3 n;
-            if (ob.x == 0) n = normalized(pt - mk(oa.x, oa.y, oa.z));
-            else {
-                const float4 n4 = __ldg(&G.obj_n[idx]);
-                n = mk(n4.x, n4.y, n4.z);
-            }
             const DevMaterial &m = G.mat[ob.z];
-
-            // ---- shading(), render.rs:1020-1140, march-mode shadow (:1052-1067) ----
-            const float light_incidence = dot(light, n);
-            const float ln2 = 2.0f * light_incidence;
-            const V3 rr_light = (n * ln2) - light;
-            const int pn = m.pn;
-            const float diffuse_intensity = fmaxf(light_incidence, 0.0f);
-            const V3 shadow_org = pt + (light * F32_EPSILON);
-            float reflection_intensity = 0.0f;
-            if (pn != 0) {
-                const float ri = -dot(rr_light, eye);
-                if (ri > 0.0f) reflection_intensity = rs_powi(ri, pn);
-            }
             float k1 = 0.2f, k2 = 0.0f;
-            {
-                const MarchResult sh = raymarch_single<false>(S, shadow_org, light, idx);
-                if (COUNT) {
-                    cnt.shadow++;
-                    cnt.march_steps += (unsigned long long)sh.iter;
-                    cnt.object_tests += (unsigned long long)sh.iter * (unsigned long long)(G.n_objects - 1);
-                    cnt.sphere_tests += (unsigned long long)sh.iter * (unsigned long long)spheres_tested(G, idx);
-                    if (ob.x == 0) cnt.sphere_hits++;
-                }
-                const bool lit = FAR_AWAY <= sh.travel_dist || MAX_ITER <= sh.iter || 0.0f < m.t;
-                if (lit) {
-                    k1 = fminf(k1 + diffuse_intensity, 1.0f);
-                    k2 = reflection_intensity;
-                }
+            const bool lit = FAR_AWAY <= r.travel_dist || MAX_ITER <= r.iter || 0.0f < m.t;
+            if (lit) {
+                k1 = fminf(k1 + diffuse_intensity, 1.0f);
+                k2 = reflection_intensity;
             }
-            float u, v;
-            get_uv(m, pt - mk(oa.x, oa.y, oa.z), ob.y, u, v);
-            const V3 kd = lookup_texture(G, m, u, v);
-            V3 face = mk(kd.x * k1 + k2, kd.y * k1 + k2, kd.z * k1 + k2);
+            const V3 kd = get_diffuse(G, m, pt - mk(oa.x, oa.y, oa.z), ob.y);
+            const V3 face = mk(kd.x * k1 + k2, kd.y * k1 + k2, kd.z * k1 + k2);
             const V3 ks = mk(m.specular[0], m.specular[1], m.specular[2]);
 
             if (lev < P.max_refractions && 0.0f < m.t) {
+                // refraction child, render.rs:1093-1115: suspend this frame
                 const float sp = dot(eye, n);
                 const float f = m.t;
                 const float frac = m.n;
@@ -210,13 +296,11 @@ __device__ __forceinline__ V3 march_pixel(const DevScene &G, const MarchView &S,
                     const V3 e2 = eye + n * en2;
                     F.pos[0] = pt.x; F.pos[1] = pt.y; F.pos[2] = pt.z;
                     F.eye[0] = e2.x; F.eye[1] = e2.y; F.eye[2] = e2.z;
-                    F.flags = dot(n, e2) < 0.0f ? OUTONLY : INONLY;
                 }
                 depth += 1;
                 pos = pt3;
                 eye = ray;
                 ig = idx;
-                flags = sp < 0.0f ? OUTONLY : INONLY;
                 ret = mk(0.0f, 0.0f, 0.0f);
                 fcs = mk(1.0f, 1.0f, 1.0f);
                 mmd = RR_INF;
@@ -232,32 +316,11 @@ __device__ __forceinline__ V3 march_pixel(const DevScene &G, const MarchView &S,
             } else {
                 pos = pt;
                 const float en2 = -2.0f * dot(eye, n);
-                eye = eye + n * en2;
-                flags = dot(n, eye) < 0.0f ? OUTONLY : INONLY;
+                eye = eye + n * en2;  // (flags are recomputed by the reference here but distance() ignores them)
                 ig = idx;
                 ray_class = 2;
-                frame_done = false;  // lev < MAX_REFLECTIONS here, so render.rs:1391 does not break
             }
-        } else {
-            // Miss (render.rs:1385-1393): bg is added and, because pos/eye/ig are unchanged, the very
-            // same march repeats until lev reaches MAX_REFLECTIONS. The repeats are bit-identical, so
-            // the march result is reused and only the accumulation is replayed (appendix A Q15).
-            const V3 bg = bgcolor(P, eye);
-            for (;;) {
-                if (COUNT) cnt.bg_evals++;
-                ret = mk(ret.x + bg.x * fcs.x, ret.y + bg.y * fcs.y, ret.z + bg.z * fcs.z);
-                if (MAX_REFLECTIONS_CONST <= lev) break;
-                lev += 1;
-                if (COUNT) {  // the reference re-marches here
-                    cnt.reflect++;
-                    cnt.march_steps += (unsigned long long)r.iter;
-                    cnt.object_tests += (unsigned long long)r.iter * (unsigned long long)(G.n_objects - (ig >= 0 ? 1 : 0));
-                    cnt.sphere_tests += (unsigned long long)r.iter * (unsigned long long)spheres_tested(G, ig);
-                }
-            }
-            frame_done = true;
         }
-        (void)flags;
 
         while (frame_done) {
             const V3 val = apply_glow(P, ret, mmd);  // each raymarch() call applies its own factor
@@ -273,7 +336,6 @@ __device__ __forceinline__ V3 march_pixel(const DevScene &G, const MarchView &S,
                 fcs = mk(F.fcs[0] * pm.specular[0], F.fcs[1] * pm.specular[1], F.fcs[2] * pm.specular[2]);
                 pos = mk(F.pos[0], F.pos[1], F.pos[2]);
                 eye = mk(F.eye[0], F.eye[1], F.eye[2]);
-                flags = F.flags;
                 ig = F.ig;
                 lev = F.lev;
                 ray_class = 2;

@@ -99,12 +99,13 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
         if (valid) c = trace_pixel<COUNT, BVH>(G, H, S, P, ix, local_to_image_row(P, ly), cnt);
         if (F32OUT) {
             if (valid) {
-                float *o = reinterpret_cast<float *>(out) + ((size_t)ly * W + ix) * 3;
+                float *o = reinterpret_cast<float *>(out) + ((size_t)(P.placed ? local_to_image_row(P, ly) : ly) * W + ix) * 3;
                 o[0] = c.x; o[1] = c.y; o[2] = c.z;
             }
         } else {
             const unsigned rgb = quantize(c.x) | (quantize(c.y) << 8) | (quantize(c.z) << 16);
-            store_tile_rgb8(reinterpret_cast<uint8_t *>(out), row_stride, x0, ly0, W, rows, rgb, fast_store != 0);
+            store_tile_rgb8(reinterpret_cast<uint8_t *>(out), row_stride, x0, ly0, W, rows, rgb, fast_store != 0,
+                            P.placed ? local_to_image_row(P, ly) : ly);
         }
     }
     if (COUNT) flush_counters(cnt, gcnt);

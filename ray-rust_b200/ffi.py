@@ -126,6 +126,15 @@ PROTOTYPES = {
     "rr_render_f32_device": (C.c_int, [_P, C.POINTER(rr_frame_params), _P, _P]),
     "rr_render_count": (C.c_int, [_P, C.POINTER(rr_frame_params), _P, C.c_size_t, C.POINTER(rr_ray_counts)]),
     "rr_bands_unpack_device": (C.c_int, [C.POINTER(rr_frame_params), _P, C.c_size_t, _P, _P]),
+    "rr_render_rgb8_placed_device": (C.c_int, [_P, C.POINTER(rr_frame_params), _P, C.c_size_t, _P]),
+    "rr_render_rgb8_placed": (C.c_int, [_P, C.POINTER(rr_frame_params), _P, C.c_size_t]),
+    "rr_device_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_P)]),
+    "rr_device_free": (C.c_int, [C.c_int, _P]),
+    "rr_ipc_export": (C.c_int, [_P, _P]),
+    "rr_ipc_open": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
+    "rr_ipc_close": (C.c_int, [C.c_int, _P]),
+    "rr_host_register": (C.c_int, [_P, C.c_size_t]),
+    "rr_host_unregister": (C.c_int, [_P]),
     "rr_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
     "rr_host_free": (C.c_int, [_P]),
     "rr_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),

@@ -358,3 +358,22 @@ def test_config5_8k_bands_identical_to_single(rr, oracle):
     exact, le1, mx, _ = diff_stats(full, ref)
     print(f"config5 8K: exact={exact:.6f} le1={le1:.6f} max={mx}")
     assert le1 == 1.0 and exact >= 0.9995
+
+
+def test_many_glowing_objects_march(rr, oracle):
+    """More than 4 glowing objects switches the march kernel to inline glow tracking; a glowing floor too."""
+    ren = rr.synthetic_scene(96, 54, n_spheres=48, use_raymarching=True, glow_effect=0.7)
+    seen = set()
+    for o in ren._objects:
+        if id(o.material) not in seen:
+            seen.add(id(o.material))
+            o.material.glow_dist(2.0 + 0.5 * len(seen))
+    assert len(seen) > 4
+    ref = oracle.render(ren, threads=NCPU, want_f32=True, want_tags=True)
+    exact, le1, mx, _ = diff_stats(device_render(rr, ren), ref["u8"])
+    assert le1 >= 0.999 and exact >= 0.99, (exact, le1, mx)
+    few = rr.default_scene(96, 54, use_raymarching=True, glow_effect=0.7)
+    few._objects[0].material.glow_dist(0.25)   # glowing floor + glowing red sphere: the separate glow pass
+    ref = oracle.render(few, threads=NCPU)
+    exact, le1, mx, _ = diff_stats(device_render(rr, few), ref["u8"])
+    assert le1 >= 0.999 and exact >= 0.99, (exact, le1, mx)

@@ -556,30 +556,52 @@ int rr_render_rgb8_placed(rr_scene *s, const rr_frame_params *params, uint8_t *h
     const int rows = P.local_rows;
     if (rows == 0 || P.xres == 0) return RR_OK;
     if ((rc = ensure_out(s, packed * rows))) return rc;
+    const int B = P.band_count <= 1 ? 4 : P.band_rows, n = P.band_count, k = P.band_index;
+    // Same pipeline as rr_render_rgb8: up to 8 chunks of whole bands, each chunk's device-to-host copy
+    // queued on the copy stream behind its kernel so PCIe overlaps the next chunk's rendering.
+    int nchunk = (int)((packed * rows) / (4u << 20));
+    if (nchunk < 1) nchunk = 1;
+    if (nchunk > 8) nchunk = 8;
+    if (P.use_raymarching || s->G.n_objects > 64) nchunk = 1;
+    int chunk_rows = (rows + nchunk - 1) / nchunk;
+    const int align = (B % 4 == 0) ? B : B * 4;  // whole bands and whole 4-row tiles
+    chunk_rows = ((chunk_rows + align - 1) / align) * align;
     CU(cudaEventRecord(s->ev0, s->stream));
-    if ((rc = launch(s, P, s->d_out, packed, false, nullptr, s->stream))) return rc;
-    CU(cudaEventRecord(s->ev1, s->stream));
-    const int B = P.band_rows, n = P.band_count, k = P.band_index;
-    if (n <= 1) {
-        CU(cudaMemcpy2DAsync(host_frame, row_stride, s->d_out, packed, packed, (size_t)rows, cudaMemcpyDeviceToHost, s->stream));
-    } else if (row_stride == packed) {
-        // full bands: one strided copy (a band is B contiguous rows; bands of this shard are n*B rows apart)
-        const int full = rows / B, tail = rows - full * B;
-        const size_t band_bytes = (size_t)B * packed;
-        if (full > 0)
-            CU(cudaMemcpy2DAsync(host_frame + (size_t)k * band_bytes, (size_t)n * band_bytes, s->d_out, band_bytes, band_bytes,
-                                 (size_t)full, cudaMemcpyDeviceToHost, s->stream));
-        if (tail > 0)
-            CU(cudaMemcpyAsync(host_frame + ((size_t)full * n + k) * band_bytes, reinterpret_cast<uint8_t *>(s->d_out) + (size_t)full * band_bytes,
-                               (size_t)tail * packed, cudaMemcpyDeviceToHost, s->stream));
-    } else {
-        for (int r0 = 0; r0 < rows; r0 += B) {  // padded rows: one 2D copy per band
-            const int nr = rows - r0 < B ? rows - r0 : B;
-            const size_t iy = ((size_t)(r0 / B) * n + k) * B;
-            CU(cudaMemcpy2DAsync(host_frame + iy * row_stride, row_stride, reinterpret_cast<uint8_t *>(s->d_out) + (size_t)r0 * packed, packed,
-                                 packed, (size_t)nr, cudaMemcpyDeviceToHost, s->stream));
+    int ci = 0;
+    for (int r0 = 0; r0 < rows; r0 += chunk_rows, ++ci) {
+        rr::FrameParams Cp = P;
+        Cp.row0 = r0;
+        Cp.local_rows = rows - r0 < chunk_rows ? rows - r0 : chunk_rows;
+        uint8_t *d = reinterpret_cast<uint8_t *>(s->d_out) + (size_t)r0 * packed;
+        if ((rc = launch(s, Cp, d, packed, false, nullptr, s->stream))) return rc;
+        CU(cudaEventRecord(s->chunk_ev[ci], s->stream));
+        CU(cudaStreamWaitEvent(s->copy_stream, s->chunk_ev[ci], 0));
+        const int nr = Cp.local_rows;
+        if (n <= 1) {
+            CU(cudaMemcpy2DAsync(host_frame + (size_t)r0 * row_stride, row_stride, d, packed, packed, (size_t)nr,
+                                 cudaMemcpyDeviceToHost, s->copy_stream));
+        } else if (row_stride == packed) {
+            // a band is B contiguous rows; this shard's bands are n*B rows apart in the frame: one strided copy
+            const int full = nr / B, tail = nr - full * B;
+            const size_t band_bytes = (size_t)B * packed;
+            const size_t first_band = (size_t)(r0 / B);
+            if (full > 0)
+                CU(cudaMemcpy2DAsync(host_frame + (first_band * n + k) * band_bytes, (size_t)n * band_bytes, d, band_bytes, band_bytes,
+                                     (size_t)full, cudaMemcpyDeviceToHost, s->copy_stream));
+            if (tail > 0)
+                CU(cudaMemcpyAsync(host_frame + ((first_band + full) * n + k) * band_bytes, d + (size_t)full * band_bytes,
+                                   (size_t)tail * packed, cudaMemcpyDeviceToHost, s->copy_stream));
+        } else {
+            for (int b0 = 0; b0 < nr; b0 += B) {  // padded rows: one 2D copy per band
+                const int br = nr - b0 < B ? nr - b0 : B;
+                const size_t iy = ((size_t)((r0 + b0) / B) * n + k) * B;
+                CU(cudaMemcpy2DAsync(host_frame + iy * row_stride, row_stride, d + (size_t)b0 * packed, packed, packed, (size_t)br,
+                                     cudaMemcpyDeviceToHost, s->copy_stream));
+            }
         }
     }
+    CU(cudaEventRecord(s->ev1, s->stream));
+    CU(cudaStreamSynchronize(s->copy_stream));
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
     s->timed = true;

@@ -1,0 +1,65 @@
+"""Placed output (multi-GPU path): shards render their row bands straight to the image rows of one frame,
+in device memory (the pointer may be NVLink peer memory in the real multi-process run) or in host memory.
+Exercised here on one GPU by letting a single process play every rank in turn."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,band,w,h,march", [(2, 16, 256, 150, False), (8, 16, 640, 360, False), (3, 4, 96, 70, True), (4, 5, 64, 37, False)])
+def test_placed_device_and_host(rr, n, band, w, h, march):
+    import torch
+
+    ren = rr.default_scene(w, h, use_raymarching=march, glow_effect=1.0 if march else None)
+    scene = rr.DeviceScene(ren, 0)
+    lib = scene.lib
+    full = scene.render_rgb8(ren.frame_params())
+    frame = torch.zeros(h * w * 3, dtype=torch.uint8, device="cuda:0")
+    host = np.zeros((h, w, 3), dtype=np.uint8)
+    for k in range(n):
+        p = ren.frame_params(band, k, n)
+        rr.ffi.check(lib.rr_render_rgb8_placed_device(scene.handle, C.byref(p), C.c_void_p(frame.data_ptr()), 0, None))
+        rr.ffi.check(lib.rr_render_rgb8_placed(scene.handle, C.byref(p), host.ctypes.data_as(C.c_void_p), 0))
+    torch.cuda.synchronize()
+    assert np.array_equal(frame.cpu().numpy().reshape(h, w, 3), full)
+    assert np.array_equal(host, full)
+    # padded host rows
+    stride = w * 3 + 12
+    padded = np.full((h, stride), 0xCD, dtype=np.uint8)
+    for k in range(n):
+        p = ren.frame_params(band, k, n)
+        rr.ffi.check(lib.rr_render_rgb8_placed(scene.handle, C.byref(p), padded.ctypes.data_as(C.c_void_p), stride))
+    assert np.array_equal(padded[:, : w * 3].reshape(h, w, 3), full) and (padded[:, w * 3:] == 0xCD).all()
+    scene.close()
+
+
+def test_placed_big_frame_chunked(rr):
+    """A frame large enough for the chunked copy pipeline (several chunks of whole bands)."""
+    ren = rr.default_scene(3840, 2160)
+    scene = rr.DeviceScene(ren, 0)
+    full = scene.render_rgb8(ren.frame_params())
+    host = np.zeros_like(full)
+    for k in range(2):
+        p = ren.frame_params(16, k, 2)
+        rr.ffi.check(scene.lib.rr_render_rgb8_placed(scene.handle, C.byref(p), host.ctypes.data_as(C.c_void_p), 0))
+    whole = np.zeros_like(full)
+    rr.ffi.check(scene.lib.rr_render_rgb8_placed(scene.handle, C.byref(ren.frame_params()), whole.ctypes.data_as(C.c_void_p), 0))
+    scene.close()
+    assert np.array_equal(host, full) and np.array_equal(whole, full)
+
+
+def test_device_alloc_and_ipc_export(rr):
+    lib = rr.ffi.load()
+    p = C.c_void_p()
+    rr.ffi.check(lib.rr_device_alloc(0, 1 << 20, C.byref(p)))
+    handle = (C.c_uint8 * 64)()
+    rr.ffi.check(lib.rr_ipc_export(p, handle))
+    assert any(handle)
+    rr.ffi.check(lib.rr_device_free(0, p))
+    assert lib.rr_ipc_export(None, handle) == rr.ffi.RR_ERR_BAD_ARG
+    buf = np.zeros(1 << 16, dtype=np.uint8)
+    rr.ffi.check(lib.rr_host_register(buf.ctypes.data_as(C.c_void_p), buf.nbytes))
+    rr.ffi.check(lib.rr_host_unregister(buf.ctypes.data_as(C.c_void_p)))

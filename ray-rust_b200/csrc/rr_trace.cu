@@ -63,18 +63,19 @@ __device__ __forceinline__ SceneView stage_scene(const DevScene &G, float4 *smem
     return S;
 }
 
-template <bool COUNT, bool F32OUT, bool STAGE, bool BVH>
+template <bool COUNT, bool F32OUT, bool STAGE, bool BVH, int TW>
 __global__ void __launch_bounds__(TRACE_THREADS, RR_TRACE_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHead H, const __grid_constant__ FrameParams P,
              void *__restrict__ out, size_t row_stride, Counters *gcnt, int fast_store, float inv_tiles_x) {
     extern __shared__ float4 rr_smem[];
     const SceneView S = stage_scene<BVH>(G, rr_smem, STAGE);
 
+    constexpr int TH = 32 / TW;  // warp tile: TW x TH pixels (8x4, or 32x1 for placed output over NVLink)
     const int W = P.xres, rows = P.local_rows;
-    const int tiles_x = (W + 7) >> 3, tiles_y = (rows + 3) >> 2;
+    const int tiles_x = (W + TW - 1) / TW, tiles_y = (rows + TH - 1) / TH;
     const int ntiles = tiles_x * tiles_y;
     const int lane = threadIdx.x & 31;
-    const int col = lane & 7, row = lane >> 3;
+    const int col = lane % TW, row = lane / TW;
     const int warps_per_block = blockDim.x >> 5;
     const int gw = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     const int nw = gridDim.x * warps_per_block;
@@ -92,7 +93,7 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
             ty = tile / tiles_x;
         }
         const int tx = tile - ty * tiles_x;
-        const int x0 = tx << 3, ly0 = ty << 2;
+        const int x0 = tx * TW, ly0 = ty * TH;
         const int ix = x0 + col, ly = ly0 + row;
         const bool valid = ix < W && ly < rows;
         V3 c = mk(0.0f, 0.0f, 0.0f);
@@ -104,8 +105,8 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
             }
         } else {
             const unsigned rgb = quantize(c.x) | (quantize(c.y) << 8) | (quantize(c.z) << 16);
-            store_tile_rgb8(reinterpret_cast<uint8_t *>(out), row_stride, x0, ly0, W, rows, rgb, fast_store != 0,
-                            P.placed ? local_to_image_row(P, ly) : ly);
+            store_tile_rgb8<TW>(reinterpret_cast<uint8_t *>(out), row_stride, x0, ly0, W, rows, rgb, fast_store != 0,
+                                P.placed ? local_to_image_row(P, ly) : ly);
         }
     }
     if (COUNT) flush_counters(cnt, gcnt);
@@ -119,10 +120,11 @@ static size_t trace_smem_bytes(const DevScene &G, bool bvh) {
     return b + ts * (sizeof(float4) + sizeof(int));
 }
 
-template <bool COUNT, bool F32OUT, bool STAGE, bool BVH>
-static cudaError_t launch_one(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
-                              Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, size_t smem) {
-    auto kern = trace_kernel<COUNT, F32OUT, STAGE, BVH>;
+template <bool COUNT, bool F32OUT, bool STAGE, bool BVH, int TW>
+static cudaError_t launch_tw(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
+                             Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, size_t smem) {
+    auto kern = trace_kernel<COUNT, F32OUT, STAGE, BVH, TW>;
+    constexpr int TH = 32 / TW;
     cudaError_t e;
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -132,16 +134,27 @@ static cudaError_t launch_one(const DevScene &G, const SceneHead &H, const Frame
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TRACE_THREADS, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    const int tiles_x = (P.xres + 7) / 8;
-    const long long tiles = (long long)tiles_x * ((P.local_rows + 3) / 4);
+    const int tiles_x = (P.xres + TW - 1) / TW;
+    const long long tiles = (long long)tiles_x * ((P.local_rows + TH - 1) / TH);
     const long long need = (tiles + (TRACE_THREADS / 32) - 1) / (TRACE_THREADS / 32);
     long long grid = (long long)li.sm_count * per_sm;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    const int fast = (!F32OUT && (P.xres % 8 == 0) && (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0)) ? 1 : 0;
+    const int fast = (!F32OUT && (P.xres % TW == 0) && (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0)) ? 1 : 0;
     const float inv_tx = tiles < (1 << 24) ? 1.0f / (float)tiles_x : 0.0f;
     kern<<<(unsigned)grid, TRACE_THREADS, smem, stream>>>(G, H, P, d_out, row_stride, d_cnt, fast, inv_tx);
     return cudaGetLastError();
+}
+
+// Tile shape: 8x4 for local output; 32x1 row tiles when the rows are placed into a (possibly peer) frame.
+template <bool COUNT, bool F32OUT, bool STAGE, bool BVH>
+static cudaError_t launch_one(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
+                              Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, size_t smem) {
+    if constexpr (!F32OUT && !COUNT) {
+        if (P.placed && P.xres % 32 == 0)
+            return launch_tw<COUNT, F32OUT, STAGE, BVH, 32>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem);
+    }
+    return launch_tw<COUNT, F32OUT, STAGE, BVH, 8>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem);
 }
 
 template <bool COUNT, bool F32OUT>

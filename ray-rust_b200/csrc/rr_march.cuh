@@ -104,9 +104,9 @@ __device__ __forceinline__ void distance_estimate(const SceneHead &H, const Marc
         // glow pass (render.rs:1244-1247) over the few glowing objects only; their distance is formed
         // with the same operations as in the scan, so the bits are the same whether or not the scan
         // above skipped the object's sqrt.
-#pragma unroll
-        for (int g = 0; g < RR_HEAD_GLOW; ++g) {
-            if (g < H.n_glow_head && H.glow_oi[g] != ig) {
+#pragma unroll 1
+        for (int g = 0; g < H.n_glow_head; ++g) {  // rolled: keeps the march loop inside the L0 I-cache
+            if (H.glow_oi[g] != ig) {
                 const float4 a = H.glow_a[g];
                 float dist;
                 if (H.glow_kind[g] == 0) {

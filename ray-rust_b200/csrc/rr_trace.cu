@@ -11,7 +11,10 @@
 
 namespace rr {
 
-constexpr int TRACE_THREADS = 256;
+#ifndef RR_TRACE_THREADS
+#define RR_TRACE_THREADS 256
+#endif
+constexpr int TRACE_THREADS = RR_TRACE_THREADS;
 #ifndef RR_TRACE_MIN_BLOCKS
 #define RR_TRACE_MIN_BLOCKS 4
 #endif
@@ -81,7 +84,15 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
     const int nw = gridDim.x * warps_per_block;
     Counters cnt = {};
 
+#ifdef RR_TRACE_PHASE_LOCK
+    // experiment: keep the warps of a block in phase (shared L0/L1.5 instruction fetches)
+    const int iters = (ntiles + nw - 1) / nw;
+    for (int it = 0, tile = gw; it < iters; ++it, tile += nw) {
+        __syncthreads();
+        if (tile >= ntiles) continue;
+#else
     for (int tile = gw; tile < ntiles; tile += nw) {
+#endif
         // ty = tile / tiles_x without an integer division: float estimate + one-step correction
         // (exact for tile < 2^24; the launcher falls back to inv_tiles_x = 0 -> integer division above that)
         int ty;

@@ -6,8 +6,11 @@
 // DynamicImage::ImageRgb8 (render.rs:251).
 #include <zlib.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "rr_host.hpp"
 
@@ -39,16 +42,55 @@ std::vector<uint8_t> encode_png_rgb8(const uint8_t *rgb, uint32_t w, uint32_t h)
     ihdr[4] = h >> 24; ihdr[5] = h >> 16; ihdr[6] = h >> 8; ihdr[7] = h;
     ihdr[8] = 8; ihdr[9] = 2; ihdr[10] = 0; ihdr[11] = 0; ihdr[12] = 0;
     chunk(out, "IHDR", ihdr, 13);
+    // The frame is cut into row stripes that are deflated concurrently (pigz scheme): every stripe is
+    // a raw-deflate stream ended with Z_SYNC_FLUSH (byte aligned, not final), the last one with
+    // Z_FINISH; concatenated behind one zlib header and closed with the combined Adler-32 they form a
+    // single valid zlib stream. Once the render takes < 1 ms the serial deflate of a 25-100 MB frame is
+    // what the reference's "Rendering time" (main.rs:316-348 includes save_buffer) would consist of.
     const size_t row = (size_t)w * 3;
-    std::vector<uint8_t> raw((row + 1) * h);
-    for (uint32_t y = 0; y < h; ++y) {
-        raw[(row + 1) * y] = 0;
-        memcpy(&raw[(row + 1) * y + 1], rgb + row * y, row);
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)32, (size_t)std::max<uint32_t>(1, h / 64)});
+    if (const char *e = getenv("RR_PNG_THREADS")) nt = std::max(1, atoi(e));
+    struct Stripe {
+        std::vector<uint8_t> z;
+        uLong adler = 1, len = 0;
+        bool ok = false;
+    };
+    std::vector<Stripe> stripes(nt);
+    auto work = [&](int k) {
+        const uint32_t y0 = (uint32_t)((uint64_t)h * k / nt), y1 = (uint32_t)((uint64_t)h * (k + 1) / nt);
+        std::vector<uint8_t> raw((row + 1) * (y1 - y0));
+        for (uint32_t y = y0; y < y1; ++y) {
+            raw[(row + 1) * (y - y0)] = 0;  // filter type 0
+            memcpy(&raw[(row + 1) * (y - y0) + 1], rgb + row * y, row);
+        }
+        Stripe &s = stripes[k];
+        s.len = (uLong)raw.size();
+        s.adler = adler32(1L, raw.data(), (uInt)raw.size());
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (deflateInit2(&zs, 1, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return;
+        s.z.resize(deflateBound(&zs, (uLong)raw.size()) + 16);
+        zs.next_in = raw.data(); zs.avail_in = (uInt)raw.size();
+        zs.next_out = s.z.data(); zs.avail_out = (uInt)s.z.size();
+        const int rc = deflate(&zs, k == nt - 1 ? Z_FINISH : Z_SYNC_FLUSH);
+        s.ok = (k == nt - 1) ? rc == Z_STREAM_END : (rc == Z_OK && zs.avail_in == 0);
+        s.z.resize(zs.total_out);
+        deflateEnd(&zs);
+    };
+    std::vector<std::thread> th;
+    for (int k = 1; k < nt; ++k) th.emplace_back(work, k);
+    work(0);
+    for (auto &t : th) t.join();
+    std::vector<uint8_t> z = {0x78, 0x01};  // zlib header: deflate, 32K window, fastest
+    uLong adler = 1;
+    for (int k = 0; k < nt; ++k) {
+        if (!stripes[k].ok) throw std::runtime_error("png: deflate failed");
+        z.insert(z.end(), stripes[k].z.begin(), stripes[k].z.end());
+        adler = k == 0 ? stripes[k].adler : adler32_combine(adler, stripes[k].adler, (z_off_t)stripes[k].len);
     }
-    uLongf cap = compressBound((uLong)raw.size());
-    std::vector<uint8_t> z(cap);
-    if (compress2(z.data(), &cap, raw.data(), (uLong)raw.size(), 1) != Z_OK) throw std::runtime_error("png: deflate failed");
-    chunk(out, "IDAT", z.data(), cap);
+    z.push_back(adler >> 24); z.push_back(adler >> 16); z.push_back(adler >> 8); z.push_back(adler);
+    chunk(out, "IDAT", z.data(), z.size());
     chunk(out, "IEND", nullptr, 0);
     return out;
 }

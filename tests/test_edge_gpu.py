@@ -1,0 +1,78 @@
+"""Degenerate inputs: the device must follow the reference's IEEE behaviour (NaN/inf propagation, saturating
+casts, f32::min/max NaN rules) exactly as the oracle does, not merely "not crash"."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+NCPU = os.cpu_count() or 1
+
+
+def _scene(rr, objs, w=96, h=64, light=(50, 60, -50), march=False, glow=None, cam=(0, -150, -300)):
+    f32 = np.float32
+    return (rr.RenderEnv.new(cam, (f32(0), -rr.scene.PI / f32(2), -rr.scene.PI / f32(2)), w, h, 1.0, f32(h) / f32(w))
+            .objects(objs).light(light).use_raymarching(march).glow_effect(glow))
+
+
+def _cmp(rr, oracle, ren, exact_f32=True):
+    ref = oracle.render(ren, threads=NCPU, want_f32=True, want_tags=True)
+    scene = rr.DeviceScene(ren, 0)
+    f = scene.render_f32(ren.frame_params())
+    u8 = scene.render_rgb8(ren.frame_params())
+    scene.close()
+    d = np.abs(u8.astype(int) - ref["u8"].astype(int)).max()
+    assert d <= 1, d
+    if exact_f32:
+        clean = (ref["tags"] & 1) == 0
+        a, b = f.view(np.uint32)[clean], ref["f32"].view(np.uint32)[clean]
+        nan_a, nan_b = np.isnan(f[clean]), np.isnan(ref["f32"][clean])
+        assert np.array_equal(nan_a, nan_b)
+        assert np.array_equal(a[~nan_a], b[~nan_b])
+
+
+def _mats(rr):
+    RC = rr.RenderColor
+    return dict(
+        floor=rr.RenderMaterial.new("floor", RC(1, 1, 0), RC(0, 0, 0), 0, 0.0, 0.0).pattern("RepeatedGradation").pattern_scale(300.0),
+        red=rr.RenderMaterial.new("red", RC(0.8, 0.1, 0.1), RC(0.2, 0.2, 0.2), 24, 0.0, 0.0),
+        glass=rr.RenderMaterial.new("glass", RC(0.1, 0.1, 0.1), RC(0.3, 0.3, 0.3), 8, 0.8, 1.5),
+        mirror=rr.RenderMaterial.new("mirror", RC(0, 0, 0), RC(1, 1, 1), 24, 0.0, 0.0),
+        negpn=rr.RenderMaterial.new("negpn", RC(0.5, 0.5, 0.9), RC(0.1, 0.1, 0.1), -3, 0.0, 0.0),      # powi with a negative exponent
+        zeroscale=rr.RenderMaterial.new("zs", RC(0.5, 0.9, 0.5), RC(0, 0, 0), 4, 0.0, 0.0).pattern("Checkerboard").pattern_scale(0.0),
+        nzero=rr.RenderMaterial.new("nzero", RC(0.1, 0.1, 0.1), RC(0, 0, 0), 0, 0.9, 0.0),              # 1/frac with frac = 0
+    )
+
+
+@pytest.mark.parametrize("march", [False, True])
+def test_degenerate_objects(rr, oracle, march):
+    m = _mats(rr)
+    objs = [
+        rr.RenderFloor.new_raw(m["floor"], (0, -300, 0), (0, 1, 0)).uvmap("ZX"),
+        rr.RenderSphere.new(m["red"], -60.0, (-150, -100, 150)),        # negative radius
+        rr.RenderSphere.new(m["mirror"], 0.0, (0, -100, 100)),          # zero radius
+        rr.RenderSphere.new(m["glass"], 2000.0, (0, -150, -300)),       # camera inside a huge glass sphere
+        rr.RenderSphere.new(m["negpn"], 70.0, (150, -120, 200)),
+        rr.RenderSphere.new(m["zeroscale"], 50.0, (-40, -220, 60)),     # uv = x/0 -> inf/NaN -> floor() as i32 saturates
+        rr.RenderSphere.new(m["nzero"], 45.0, (60, -240, 40)),
+        rr.RenderFloor.new_raw(m["red"], (0, 0, 1500), (0.0, 0.0, 0.0)),  # zero normal: w == 0 -> 0/0
+    ]
+    _cmp(rr, oracle, _scene(rr, objs, march=march, glow=0.5 if march else None))
+
+
+def test_zero_light_and_huge_coordinates(rr, oracle):
+    m = _mats(rr)
+    objs = [rr.RenderFloor.new_raw(m["floor"], (0, -300, 0), (0, 1, 0)).uvmap("ZX"),
+            rr.RenderSphere.new(m["mirror"], 80.0, (0, -30, 172)), rr.RenderSphere.new(m["glass"], 100.0, (70, -200, 150))]
+    _cmp(rr, oracle, _scene(rr, objs, light=(0, 0, 0)), exact_f32=True)          # normalized(0) = NaN light
+    far = [rr.RenderFloor.new_raw(m["floor"], (0, -3e30, 0), (0, 1, 0)).uvmap("ZX"),
+           rr.RenderSphere.new(m["red"], 1e19, (0, 0, 3e19)), rr.RenderSphere.new(m["glass"], 1e-30, (0, -150, -299))]
+    _cmp(rr, oracle, _scene(rr, far))                                            # overflow to inf inside the tests
+
+
+def test_nan_camera(rr, oracle):
+    m = _mats(rr)
+    objs = [rr.RenderFloor.new_raw(m["floor"], (0, -300, 0), (0, 1, 0)).uvmap("ZX"), rr.RenderSphere.new(m["red"], 80.0, (0, -30, 172))]
+    ren = _scene(rr, objs, w=16, h=8)
+    ren.camera.position = (np.float32("nan"), np.float32(0), np.float32(0))
+    _cmp(rr, oracle, ren)

@@ -388,6 +388,24 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_s.item()) * 1e3 / e2e_steps
     e2e_value = rays / (e2e_ms * 1e-3) / 1e6
+    # what bounds e2e: the frame has to cross PCIe once. Raw pinned D2H bandwidth of the same byte count, same box.
+    pcie = None
+    if not sharded:
+        pin = torch.empty(frame_bytes, dtype=torch.uint8).pin_memory()
+        src = torch.empty(frame_bytes, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            pin.copy_(src, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(10):
+            pin.copy_(src, non_blocking=True)
+        c1.record(stream)
+        torch.cuda.synchronize(dev)
+        raw_ms = c0.elapsed_time(c1) / 10
+        pcie = {"bound": "pcie-d2h", "bytes": frame_bytes, "raw_copy_ms": raw_ms, "raw_copy_gbs": frame_bytes / raw_ms / 1e6,
+                "achieved_gbs": frame_bytes / e2e_ms / 1e6, "frac": raw_ms / e2e_ms}
+        del pin, src
     e2e_check = None
     if sharded:
         if rank == 0:
@@ -481,7 +499,7 @@ def main():
                 "d2h_bytes_per_step": my_rows * W * 3,
                 "api": ("rr_render_rgb8_placed (C ABI): each rank's bands -> one shared page-locked host frame, + barrier"
                         if sharded else "rr_render_rgb8 (C ABI) -> pinned host RGB8 frame"),
-                "check": e2e_check},
+                "check": e2e_check, "roofline": pcie},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,

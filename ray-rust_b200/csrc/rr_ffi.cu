@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -54,7 +55,7 @@ struct rr_scene {
     rr::Counters *d_cnt = nullptr;
     unsigned *d_work = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t chunk_ev[8] = {};
+    cudaEvent_t chunk_ev[32] = {};
     float last_ms = 0.0f;
     bool timed = false;
     bool culling = true;
@@ -185,6 +186,20 @@ bool build_bvh(const std::vector<float4> &sph_m, Bvh &out) {
     }
     out.r_min = rmin;
     return true;
+}
+
+// How many row chunks a host-bound frame is cut into (kernel of chunk k+1 overlaps the copy of chunk k).
+// Defaults measured on B200 + PCIe Gen5 (profiles/r1e_e2e_chunks.md); RR_E2E_MAX_CHUNKS / RR_E2E_CHUNK_KB override.
+int pick_chunks(size_t bytes, const rr::FrameParams &P, const rr_scene *s) {
+    static const int max_chunks = [] { const char *e = getenv("RR_E2E_MAX_CHUNKS"); int v = e ? atoi(e) : 16; return v < 1 ? 1 : (v > 32 ? 32 : v); }();
+    static const size_t chunk_bytes = [] { const char *e = getenv("RR_E2E_CHUNK_KB"); long v = e ? atol(e) : 1536; return (size_t)(v < 64 ? 64 : v) << 10; }();
+    // Chunking pays only while the kernel is shorter than the copy. Long kernels (ray marching with its
+    // heavy-tailed rows, scenes with many objects) lose more to per-chunk tails than the overlap wins.
+    if (P.use_raymarching || s->G.n_objects > 64) return 1;
+    long long n = (long long)(bytes / chunk_bytes);
+    if (n < 1) n = 1;
+    if (n > max_chunks) n = max_chunks;
+    return (int)n;
 }
 
 int ensure_out(rr_scene *s, size_t bytes) {
@@ -432,13 +447,7 @@ int rr_render_rgb8(rr_scene *s, const rr_frame_params *params, uint8_t *out, siz
     const int rows = P.local_rows;
     if (rows == 0 || P.xres == 0) return RR_OK;
     if ((rc = ensure_out(s, packed * rows))) return rc;
-    int nchunk = (int)((packed * rows) / (4u << 20));  // ~4 MiB per chunk, at most 8 chunks
-    if (nchunk < 1) nchunk = 1;
-    if (nchunk > 8) nchunk = 8;
-    // Chunking pays only while the kernel is shorter than the copy. Long kernels (ray marching with
-    // its heavy-tailed rows, scenes with many objects) lose more to per-chunk tails than the
-    // overlap wins: render those in one launch.
-    if (P.use_raymarching || s->G.n_objects > 64) nchunk = 1;
+    const int nchunk = pick_chunks(packed * rows, P, s);
     int chunk_rows = (rows + nchunk - 1) / nchunk;
     chunk_rows = (chunk_rows + 3) & ~3;  // whole 4-row tiles
     CU(cudaEventRecord(s->ev0, s->stream));
@@ -451,8 +460,11 @@ int rr_render_rgb8(rr_scene *s, const rr_frame_params *params, uint8_t *out, siz
         if ((rc = launch(s, C, d, packed, false, nullptr, s->stream))) return rc;
         CU(cudaEventRecord(s->chunk_ev[k], s->stream));
         CU(cudaStreamWaitEvent(s->copy_stream, s->chunk_ev[k], 0));
-        CU(cudaMemcpy2DAsync(out + (size_t)r0 * row_stride, row_stride, d, packed, packed, (size_t)C.local_rows,
-                             cudaMemcpyDeviceToHost, s->copy_stream));
+        if (row_stride == packed)  // contiguous rows: plain 1-D copy
+            CU(cudaMemcpyAsync(out + (size_t)r0 * packed, d, packed * (size_t)C.local_rows, cudaMemcpyDeviceToHost, s->copy_stream));
+        else
+            CU(cudaMemcpy2DAsync(out + (size_t)r0 * row_stride, row_stride, d, packed, packed, (size_t)C.local_rows,
+                                 cudaMemcpyDeviceToHost, s->copy_stream));
     }
     CU(cudaEventRecord(s->ev1, s->stream));
     CU(cudaStreamSynchronize(s->copy_stream));
@@ -559,10 +571,7 @@ int rr_render_rgb8_placed(rr_scene *s, const rr_frame_params *params, uint8_t *h
     const int B = P.band_count <= 1 ? 4 : P.band_rows, n = P.band_count, k = P.band_index;
     // Same pipeline as rr_render_rgb8: up to 8 chunks of whole bands, each chunk's device-to-host copy
     // queued on the copy stream behind its kernel so PCIe overlaps the next chunk's rendering.
-    int nchunk = (int)((packed * rows) / (4u << 20));
-    if (nchunk < 1) nchunk = 1;
-    if (nchunk > 8) nchunk = 8;
-    if (P.use_raymarching || s->G.n_objects > 64) nchunk = 1;
+    const int nchunk = pick_chunks(packed * rows, P, s);
     int chunk_rows = (rows + nchunk - 1) / nchunk;
     const int align = (B % 4 == 0) ? B : B * 4;  // whole bands and whole 4-row tiles
     chunk_rows = ((chunk_rows + align - 1) / align) * align;

@@ -93,16 +93,17 @@ __device__ __forceinline__ void sphere_test(const float4 &c4, OiFn get_oi, const
 // same bit-exact sphere_test(); only the decision to skip uses other arithmetic, with margins:
 //   * rounding analysis of the reference's q = D*D - (wpt.wpt - r*r): |q_f32 - q_true| <= 21 u d^2
 //     (u = 2^-24, d = |origin - centre|), so a sphere the f32 test can hit lies within
-//     sqrt(r^2 + K d^2) of the ray with K = 1.25e-6. Boxes are inflated per ray by
-//     e = sqrt(r_min^2 + M D^2) - r_min + 1e-6 D, M = 6e-6 (4.8 K), D = largest distance from the ray
-//     origin to the scene bounds; the same inflation bounds |t_f32 - t_true| for the entry test.
+//     sqrt(r^2 + K d^2) of the ray with K = 1.25e-6; a direction of squared length 1 + delta
+//     (|delta| <= 4e-6, checked per ray in raycast) adds delta*c <= 4e-6 d^2. Boxes are inflated per ray by
+//     e = sqrt(r_min^2 + M D^2) - r_min + 1e-6 D, M = 1.2e-5 (2.3x the 5.25e-6 total), D = largest distance
+//     from the ray origin to the scene bounds; the same inflation bounds |t_f32 - t_true| for the entry test.
 //   * slab arithmetic itself gets 1e-6 relative slack on both interval ends.
 // Ties keep the reference rule (lowest original index) because leaves apply the full lexicographic
 // comparison whatever the visiting order. Verified bit-for-bit against the brute-force oracle in
 // tests/test_parity_gpu.py (synthetic scenes, all depth limits) and against the brute-force
 // kernel instance in tests/test_bvh_gpu.py.
 // ---------------------------------------------------------------------------------------------
-constexpr float RR_BVH_M = 6e-6f;
+constexpr float RR_BVH_M = 1.2e-5f;
 
 __device__ __forceinline__ void bvh_scan(const DevScene &G, const SceneView &S, const V3 &vi, const V3 &eye, int ig,
                                          bool near_ok, bool far_ok, float &t, int &idx) {
@@ -162,7 +163,18 @@ __device__ __forceinline__ Hit raycast(const DevScene &G, const SceneHead &H, co
     const bool near_ok = (flags & OUTONLY) == 0;
     const bool far_ok = (flags & INONLY) == 0;
     if (BVH) {
-        bvh_scan(G, S, vi, eye, ig, near_ok, far_ok, t, idx);
+        // The cull is geometric; the reference's test is geometric only for unit directions (it drops the
+        // |eye|^2 factor of the quadratic). Directions are unit to a few ulp everywhere except after a bounce
+        // off an un-normalised floor normal (face_normal is used as given, render.rs:553-563, appendix A Q22),
+        // where eye += n*(-2 eye.n) changes its length. Such rays (and NaN directions) scan every sphere.
+        // |eye|^2 = 1 + delta perturbs the discriminant by delta*c <= 4e-6 d^2, inside the margin M (rr_trace.cuh).
+        const float e2 = dot(eye, eye);
+        if (fabsf(e2 - 1.0f) <= 4e-6f) {
+            bvh_scan(G, S, vi, eye, ig, near_ok, far_ok, t, idx);
+        } else {
+            for (int s = 0; s < S.n_spheres; ++s)
+                sphere_test(S.bsph[s], [&] { return S.bsph_oi[s]; }, vi, eye, ig, near_ok, far_ok, t, idx);
+        }
         return Hit{t, idx};
     }
 #pragma unroll

@@ -22,7 +22,7 @@ def _both(rr, ren):
     return a, b, a8, b8
 
 
-def _random_scene(rr, seed, n, w=192, h=108, spread=1.0, tiny=False, dup=False, inside=False):
+def _random_scene(rr, seed, n, w=192, h=108, spread=1.0, tiny=False, dup=False, inside=False, badfloor=False):
     rng = np.random.default_rng(seed)
     RC = rr.RenderColor
     floor = rr.RenderMaterial.new("floor", RC(1, 1, 0), RC(0, 0, 0), 0, 0.0, 0.0).pattern("RepeatedGradation").pattern_scale(300.0)
@@ -44,17 +44,24 @@ def _random_scene(rr, seed, n, w=192, h=108, spread=1.0, tiny=False, dup=False, 
         objs.append(rr.RenderSphere.new(mats[rng.integers(len(mats))], r, c))
         if dup and k % 5 == 0:   # an exact duplicate with another material: the lower index must win every tie
             objs.append(rr.RenderSphere.new(mats[rng.integers(len(mats))], r, c))
+    if badfloor:
+        # an un-normalised floor normal that is not object 0: bounces off it change |eye| (appendix A Q22), the
+        # reference's sphere test then is no longer the geometric one and such rays must bypass the BVH
+        objs.insert(len(objs) // 2, rr.RenderFloor.new_raw(mats[0], (20, -310, -48), (-0.47, 0.82, 1.31)).uvmap("XY"))
     if inside:
         objs.append(rr.RenderSphere.new(mats[2], 500.0, (0, -150, -300)))  # the camera sits inside a glass sphere
     f32 = np.float32
-    return (rr.RenderEnv.new((0, -150, -300), (f32(0), -rr.scene.PI / f32(2), -rr.scene.PI / f32(2)), w, h, 1.0, f32(h) / f32(w))
-            .objects(objs).light((50, 60, -50)))
+    ren = (rr.RenderEnv.new((0, -150, -300), (f32(0), -rr.scene.PI / f32(2), -rr.scene.PI / f32(2)), w, h, 1.0, f32(h) / f32(w))
+           .objects(objs).light((50, 60, -50)))
+    if badfloor:
+        ren.max_reflections = 5
+    return ren
 
 
 @pytest.mark.parametrize("kw", [
     dict(seed=1, n=30), dict(seed=2, n=200), dict(seed=3, n=500, tiny=True), dict(seed=4, n=300, dup=True),
     dict(seed=5, n=100, spread=40.0), dict(seed=6, n=150, inside=True), dict(seed=7, n=1500, w=128, h=72),
-    dict(seed=8, n=64, spread=0.05),
+    dict(seed=8, n=64, spread=0.05), dict(seed=9, n=120, badfloor=True), dict(seed=10, n=400, badfloor=True, dup=True),
 ])
 def test_bvh_equals_bruteforce_bits(rr, kw):
     a, b, a8, b8 = _both(rr, _random_scene(rr, **kw))

@@ -2,7 +2,7 @@
 //   ray-rust <width> <height> [-t N] [-o out.png] [-m] [-g G] [-s scene.yaml] [-d scene.yaml] [--gpu D]
 // Same positional arguments, flags, defaults and console output as the reference binary. `-t` is
 // parsed and echoed but has no effect (the GPU grid replaces the row-scheduler threads). `-w/-p`
-// (web server) are recognised and refused like a reference build without the `webserver` feature.
+// start the web front-end of webserver.rs on the resident device scene (rr_web.cpp).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -21,7 +21,7 @@ static void usage() {
             "    -g, --gloweffect <gloweffect>             Enable glow effect and set its strength when ray marching method is used\n"
             "    -s, --serialize_file <serialize_file>     File name for serialized scene output\n"
             "    -d, --deserialize_file <deserialize_file> File name for deserialized scene input\n"
-            "    -w, --webserver                           (not built)\n"
+            "    -w, --webserver                           Launch a web server that responds with rendered images\n"
             "    -p, --port_no <port_no>                   [default: 3000]\n"
             "        --gpu <index>                         CUDA device [default: 0]\n");
 }
@@ -76,9 +76,10 @@ int main(int argc, char **argv) {
             ss << f.rdbuf();
             ren.deserialize(ss.str());
         }
-        if (webserver) {  // main.rs:297-309 without the `webserver` feature
-            fprintf(stderr, "Error: Web server is not enabled in build config\n");
-            return 1;
+        if (webserver) {  // main.rs:297-309
+            printf("Value for port_no: %s\n", port.c_str());
+            setvbuf(stdout, nullptr, _IOLBF, 0);
+            return rr::run_webserver(ren, (int)width, (int)height, atoi(port.c_str()), atoi(gpu.c_str()));
         }
         if (have_ser) {  // main.rs:311-314
             std::ofstream f(ser, std::ios::binary);

@@ -200,6 +200,9 @@ void render_frames(RenderEnv &ren, size_t width, size_t height,
 RenderEnv default_scene(int width, int height, bool use_raymarching, bool glow_some, float glow_value);
 RenderEnv synthetic_scene(int width, int height, int n_spheres = 1024, uint64_t seed = 20261018ull);
 
+// run_webserver(), webserver.rs:324-333: serves /, /image, /render?x&y&z&yaw&pitch from the resident device scene
+int run_webserver(const RenderEnv &ren, int width, int height, int port, int device = 0);
+
 // PNG (image::save_buffer(.., ColorType::Rgb8) / image::open for textures)
 void save_png_rgb8(const std::string &path, const uint8_t *rgb, uint32_t w, uint32_t h);
 std::vector<uint8_t> encode_png_rgb8(const uint8_t *rgb, uint32_t w, uint32_t h);

@@ -32,11 +32,12 @@ __device__ __forceinline__ SceneView stage_scene(const DevScene &G, float4 *smem
     S.n_spheres = G.n_spheres;
     S.n_floors = G.n_floors;
     S.sph = G.sph; S.sph_oi = G.sph_oi; S.flo_o = G.flo_o; S.flo_n = G.flo_n; S.flo_oi = G.flo_oi;
-    S.bvh_a = G.bvh_a; S.bvh_b = G.bvh_b; S.bsph = G.bsph; S.bsph_oi = G.bsph_oi; S.n_bvh_nodes = G.n_bvh_nodes;
+    S.bvh_a = G.bvh_a; S.bvh_b = G.bvh_b; S.bvh_w = G.bvh_w; S.bsph = G.bsph; S.bsph_oi = G.bsph_oi; S.n_bvh_nodes = G.n_bvh_nodes;
     if (!stage) return S;
     const int tf = max(G.n_floors - RR_HEAD_FLOORS, 0);
     const int ts = BVH ? 0 : max(G.n_spheres - RR_HEAD_SPHERES, 0);
-    const int nb = BVH ? G.n_bvh_nodes : 0, bs = BVH ? G.n_spheres : 0;
+    // ordered traversal: 4 float4 per inner node in ONE array (bvh_a region); depth-first arrays otherwise
+    const int nb = !BVH ? 0 : (RR_BVH_ORDERED ? 2 * G.n_bvh_inner : G.n_bvh_nodes), bs = BVH ? G.n_spheres : 0;
     if (ts + tf + nb == 0) return S;
     float4 *p = smem;
     float4 *sph = p; p += ts;
@@ -54,15 +55,19 @@ __device__ __forceinline__ SceneView stage_scene(const DevScene &G, float4 *smem
     copy_list(flo_o, G.flo_o + RR_HEAD_FLOORS, tf);
     copy_list(flo_n, G.flo_n + RR_HEAD_FLOORS, tf);
     copy_list(flo_oi, G.flo_oi + RR_HEAD_FLOORS, tf);
-    copy_list(bvh_a, G.bvh_a, nb);
-    copy_list(bvh_b, G.bvh_b, nb);
+    if (RR_BVH_ORDERED) {
+        copy_list(bvh_a, G.bvh_w, 2 * nb);  // bvh_a and bvh_b regions are adjacent: 4 * n_bvh_inner float4
+    } else {
+        copy_list(bvh_a, G.bvh_a, nb);
+        copy_list(bvh_b, G.bvh_b, nb);
+    }
     copy_list(bsph, G.bsph, bs);
     copy_list(bsph_oi, G.bsph_oi, bs);
     __syncthreads();
     // tail views are indexed with the global list index
     S.sph = sph - RR_HEAD_SPHERES; S.sph_oi = sph_oi - RR_HEAD_SPHERES;
     S.flo_o = flo_o - RR_HEAD_FLOORS; S.flo_n = flo_n - RR_HEAD_FLOORS; S.flo_oi = flo_oi - RR_HEAD_FLOORS;
-    if (BVH) { S.bvh_a = bvh_a; S.bvh_b = bvh_b; S.bsph = bsph; S.bsph_oi = bsph_oi; }
+    if (BVH) { S.bvh_a = bvh_a; S.bvh_b = bvh_b; S.bvh_w = bvh_a; S.bsph = bsph; S.bsph_oi = bsph_oi; }
     return S;
 }
 
@@ -126,7 +131,8 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
 static size_t trace_smem_bytes(const DevScene &G, bool bvh) {
     const size_t tf = G.n_floors > RR_HEAD_FLOORS ? G.n_floors - RR_HEAD_FLOORS : 0;
     size_t b = tf * (2 * sizeof(float4) + sizeof(int)) + 16;
-    if (bvh) return b + (size_t)G.n_bvh_nodes * 2 * sizeof(float4) + (size_t)G.n_spheres * (sizeof(float4) + sizeof(int));
+    const size_t node_f4 = RR_BVH_ORDERED ? (size_t)G.n_bvh_inner * 4 : (size_t)G.n_bvh_nodes * 2;
+    if (bvh) return b + node_f4 * sizeof(float4) + (size_t)G.n_spheres * (sizeof(float4) + sizeof(int));
     const size_t ts = G.n_spheres > RR_HEAD_SPHERES ? G.n_spheres - RR_HEAD_SPHERES : 0;
     return b + ts * (sizeof(float4) + sizeof(int));
 }

@@ -27,7 +27,7 @@ struct SceneView {
     const int *flo_oi;
     int n_spheres, n_floors;  // totals (head + tail)
     // BVH mode (scenes with many spheres): nodes and the leaf-ordered sphere copy
-    const float4 *bvh_a, *bvh_b, *bsph;
+    const float4 *bvh_a, *bvh_b, *bvh_w, *bsph;
     const int *bsph_oi;
     int n_bvh_nodes;
 };
@@ -149,6 +149,94 @@ __device__ __forceinline__ void bvh_scan(const DevScene &G, const SceneView &S, 
     }
 }
 
+// Ordered variant (the default): front-to-back traversal with a short per-thread stack. An inner node holds BOTH
+// child boxes (4 x float4, DevScene::bvh_w); both are tested when the node is visited, the nearer child is entered
+// first and the farther one is pushed together with its entry distance, so that after a hit has shortened t the
+// stacked subtrees beyond it are dropped without touching their nodes. The reject rule, its margins and the leaf test
+// are those of bvh_scan(); the visiting order cannot change the result because sphere_test() applies the full
+// (t, original index) comparison. Child reference: >= 0 inner node, < 0 leaf ~((first << 3) | count).
+
+// Slab arithmetic of the ordered traversal: t = plane * (1/d) - (o +- e) * (1/d) as ONE fused multiply-add per plane
+// (cull-only arithmetic, so contraction is allowed). Its rounding differs from (plane - o) * (1/d): the product
+// (o +- e) * (1/d) is rounded on its own, an absolute error of 2^-24 |o| in position space that does not shrink when the
+// plane is close to the origin. It is covered by inflating e by 4e-7 * max|o_k| (3.3x the two roundings involved);
+// the final rounding of t (2^-24 |t d| <= 6e-8 D) and the reciprocal's error stay inside the 1e-6 D term of e.
+// reject <=> min(tmax, t) < max(tmin, 0)   (t >= 0 always; a NaN slab distance is ignored by fminf/fmaxf = no cull).
+struct BoxT { float lo, hi; };
+__device__ __forceinline__ BoxT slab_pair(float lox, float loy, float loz, float hix, float hiy, float hiz, float ix, float iy, float iz,
+                                          float cx_lo, float cy_lo, float cz_lo, float cx_hi, float cy_hi, float cz_hi, float t) {
+    const float t1x = __fmaf_rn(lox, ix, -cx_lo), t2x = __fmaf_rn(hix, ix, -cx_hi);
+    const float t1y = __fmaf_rn(loy, iy, -cy_lo), t2y = __fmaf_rn(hiy, iy, -cy_hi);
+    const float t1z = __fmaf_rn(loz, iz, -cz_lo), t2z = __fmaf_rn(hiz, iz, -cz_hi);
+    BoxT r;
+    r.lo = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fmaxf(fminf(t1z, t2z), 0.0f));
+    r.hi = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fminf(fmaxf(t1z, t2z), t));
+    return r;
+}
+
+__device__ __forceinline__ void bvh_scan_ordered(const DevScene &G, const SceneView &S, const V3 &vi, const V3 &eye, int ig,
+                                                 bool near_ok, bool far_ok, float &t, int &idx) {
+    const float Dx = fmaxf(fabsf(vi.x - G.scene_lo[0]), fabsf(vi.x - G.scene_hi[0]));
+    const float Dy = fmaxf(fabsf(vi.y - G.scene_lo[1]), fabsf(vi.y - G.scene_hi[1]));
+    const float Dz = fmaxf(fabsf(vi.z - G.scene_lo[2]), fabsf(vi.z - G.scene_hi[2]));
+    const float D2 = __fmaf_rn(Dx, Dx, __fmaf_rn(Dy, Dy, Dz * Dz));
+    const float D = sqrtf(D2);
+    const float e = sqrtf(__fmaf_rn(RR_BVH_M, D2, G.r_min * G.r_min)) - G.r_min + 1e-6f * D +
+                    4e-7f * fmaxf(fmaxf(fabsf(vi.x), fabsf(vi.y)), fabsf(vi.z));
+    const float ex = fabsf(eye.x) < 1e-30f ? copysignf(1e-30f, eye.x) : eye.x;
+    const float ey = fabsf(eye.y) < 1e-30f ? copysignf(1e-30f, eye.y) : eye.y;
+    const float ez = fabsf(eye.z) < 1e-30f ? copysignf(1e-30f, eye.z) : eye.z;
+    const float ix = __frcp_rn(ex), iy = __frcp_rn(ey), iz = __frcp_rn(ez);
+    // lo planes are moved out by -e, hi planes by +e: (lo - e - o) * i = lo * i - (o + e) * i
+    const float cx_lo = (vi.x + e) * ix, cy_lo = (vi.y + e) * iy, cz_lo = (vi.z + e) * iz;
+    const float cx_hi = (vi.x - e) * ix, cy_hi = (vi.y - e) * iy, cz_hi = (vi.z - e) * iz;
+    constexpr int DONE = 0x7fffffff;
+    int stk_ref[RR_BVH_STACK];
+    float stk_t[RR_BVH_STACK];
+    int sp = 0, cur = 0;
+    // pop the next stacked subtree that can still hold a winner (entered at or before the current best hit)
+    auto pop = [&]() {
+        float tm;
+        do {
+            if (sp == 0) { cur = DONE; return; }
+            sp -= 1;
+            cur = stk_ref[sp];
+            tm = stk_t[sp];
+        } while (tm > t);  // NaN: visit
+    };
+    while (cur != DONE) {
+        // inner nodes until this lane holds a leaf (the warp leaves the loop when every lane does: leaf tests then
+        // run with more lanes active than in an if/else per step)
+        while ((unsigned)cur < (unsigned)DONE) {
+            const float4 n0 = S.bvh_w[4 * cur], n1 = S.bvh_w[4 * cur + 1], n2 = S.bvh_w[4 * cur + 2], n3 = S.bvh_w[4 * cur + 3];
+            const BoxT L = slab_pair(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ix, iy, iz, cx_lo, cy_lo, cz_lo, cx_hi, cy_hi, cz_hi, t);
+            const BoxT R = slab_pair(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ix, iy, iz, cx_lo, cy_lo, cz_lo, cx_hi, cy_hi, cz_hi, t);
+            const bool rej_l = L.hi < L.lo, rej_r = R.hi < R.lo;
+            const int l = __float_as_int(n3.x), r = __float_as_int(n3.y);
+            if (!rej_l && !rej_r) {
+                const bool left_first = L.lo <= R.lo;
+                stk_ref[sp] = left_first ? r : l;
+                stk_t[sp] = left_first ? R.lo : L.lo;
+                sp += 1;
+                cur = left_first ? l : r;
+            } else if (!rej_l) {
+                cur = l;
+            } else if (!rej_r) {
+                cur = r;
+            } else {
+                pop();
+            }
+        }
+        if (cur != DONE) {
+            const int leaf = ~cur;
+            const int first = leaf >> 3, count = leaf & 7;
+            for (int k = 0; k < count; ++k)
+                sphere_test(S.bsph[first + k], [&] { return S.bsph_oi[first + k]; }, vi, eye, ig, near_ok, far_ok, t, idx);
+            pop();
+        }
+    }
+}
+
 // scene-level raycast, render.rs:993-1018
 template <bool BVH>
 __device__ __forceinline__ Hit raycast(const DevScene &G, const SceneHead &H, const SceneView &S, const V3 &vi, const V3 &eye,
@@ -162,7 +250,7 @@ __device__ __forceinline__ Hit raycast(const DevScene &G, const SceneHead &H, co
         floor_test(S.flo_o[f], S.flo_n[f], S.flo_oi[f], vi, eye, ig, t, idx);
     const bool near_ok = (flags & OUTONLY) == 0;
     const bool far_ok = (flags & INONLY) == 0;
-    if (BVH) {
+    if constexpr (BVH) {
         // The cull is geometric; the reference's test is geometric only for unit directions (it drops the
         // |eye|^2 factor of the quadratic). Directions are unit to a few ulp everywhere except after a bounce
         // off an un-normalised floor normal (face_normal is used as given, render.rs:553-563, appendix A Q22),
@@ -170,19 +258,23 @@ __device__ __forceinline__ Hit raycast(const DevScene &G, const SceneHead &H, co
         // |eye|^2 = 1 + delta perturbs the discriminant by delta*c <= 4e-6 d^2, inside the margin M (rr_trace.cuh).
         const float e2 = dot(eye, eye);
         if (fabsf(e2 - 1.0f) <= 4e-6f) {
+#if RR_BVH_ORDERED
+            bvh_scan_ordered(G, S, vi, eye, ig, near_ok, far_ok, t, idx);
+#else
             bvh_scan(G, S, vi, eye, ig, near_ok, far_ok, t, idx);
+#endif
         } else {
             for (int s = 0; s < S.n_spheres; ++s)
                 sphere_test(S.bsph[s], [&] { return S.bsph_oi[s]; }, vi, eye, ig, near_ok, far_ok, t, idx);
         }
-        return Hit{t, idx};
-    }
+    } else {
 #pragma unroll
-    for (int s = 0; s < RR_HEAD_SPHERES; ++s)
-        if (s < S.n_spheres) sphere_test(H.sph[s], [&] { return H.sph_oi[s]; }, vi, eye, ig, near_ok, far_ok, t, idx);
+        for (int s = 0; s < RR_HEAD_SPHERES; ++s)
+            if (s < S.n_spheres) sphere_test(H.sph[s], [&] { return H.sph_oi[s]; }, vi, eye, ig, near_ok, far_ok, t, idx);
 #pragma unroll 4
-    for (int s = RR_HEAD_SPHERES; s < S.n_spheres; ++s)
-        sphere_test(S.sph[s], [&] { return S.sph_oi[s]; }, vi, eye, ig, near_ok, far_ok, t, idx);
+        for (int s = RR_HEAD_SPHERES; s < S.n_spheres; ++s)
+            sphere_test(S.sph[s], [&] { return S.sph_oi[s]; }, vi, eye, ig, near_ok, far_ok, t, idx);
+    }
     return Hit{t, idx};
 }
 

@@ -255,14 +255,20 @@ def main():
     out = None
     if sharded:
         handle = (C.c_uint8 * 64)()
+        # one allocation on rank 0: the frame, then the completion words (one uint32 per rank) and a status word
+        flags_off = (frame_bytes + 255) // 256 * 256
         if rank == 0:
-            rr.ffi.check(lib.rr_device_alloc(local_rank, frame_bytes, C.byref(frame_ptr)))
+            rr.ffi.check(lib.rr_device_alloc(local_rank, flags_off + 512, C.byref(frame_ptr)))
+            rr.ffi.check(lib.rr_device_memset(local_rank, C.c_void_p(frame_ptr.value + flags_off), 0, 512))
             rr.ffi.check(lib.rr_ipc_export(frame_ptr, handle))
         box = [bytes(handle)]
         dist.broadcast_object_list(box, src=0)
         if rank != 0:
             hb = (C.c_uint8 * 64).from_buffer_copy(box[0])
             rr.ffi.check(lib.rr_ipc_open(local_rank, hb, C.byref(frame_ptr)))
+        flags_ptr = C.c_void_p(frame_ptr.value + flags_off)
+        status_ptr = C.c_void_p(frame_ptr.value + flags_off + 256)
+        epoch = [0]
         tok = torch.zeros(1, dtype=torch.float32, device=dev)
         packed = torch.empty(shard_bytes, dtype=torch.uint8, device=dev)
         gathered = torch.empty(world * shard_bytes, dtype=torch.uint8, device=dev) if rank == 0 else None
@@ -275,6 +281,16 @@ def main():
         if not sharded:
             scene.render_rgb8_device(p, out.data_ptr(), stream=stream.cuda_stream)
             return 1
+        # fused: the render kernel stores its rows into rank 0's frame over NVLink AND publishes its completion word
+        # there; rank 0's stream waits on the words. No collective in the step.
+        epoch[0] += 1
+        rr.ffi.check(lib.rr_render_rgb8_placed_signal_device(scene.handle, C.byref(p), frame_ptr, W * 3, flags_ptr, epoch[0], sptr))
+        if rank == 0:
+            rr.ffi.check(lib.rr_fence_wait_device(local_rank, flags_ptr, world, epoch[0], 5000, status_ptr, sptr))
+            return 2
+        return 1
+
+    def step_allreduce_fence():
         rr.ffi.check(lib.rr_render_rgb8_placed_device(scene.handle, C.byref(p), frame_ptr, W * 3, sptr))
         dist.all_reduce(tok)  # completion fence: rank 0's stream passes it only after every rank's kernel
         return 1
@@ -337,20 +353,31 @@ def main():
     if sharded:
         gms, _, _, _ = timed(step_gather, max(5, args.steps // 2), False)
         alt = {"method": "nccl gather to rank 0 + rr_bands_unpack_device", "ms_per_step": gms, "value": rays / (gms * 1e-3) / 1e6}
-        # the N-GPU frame must be byte-identical to the 1-GPU frame (and the two assembly methods must agree)
+        ams, _, _, _ = timed(step_allreduce_fence, max(5, args.steps // 2), False)
+        alt = [alt, {"method": "placed NVLink stores + 1-element NCCL all-reduce as the completion fence", "ms_per_step": ams,
+                     "value": rays / (ams * 1e-3) / 1e6}]
+        # The N-GPU frame must be byte-identical to the 1-GPU frame (and the two assembly methods must agree).
+        # The fused completion signal is what orders the copy below: rank 0 clears the frame, everybody renders once,
+        # and rank 0 copies the frame out ON ITS STREAM right behind the wait kernel, with no host-side barrier between.
+        if rank == 0:
+            rr.ffi.check(lib.rr_device_memset(local_rank, frame_ptr, 0, frame_bytes))
+        barrier()
         step_main()
+        peer = None
+        if rank == 0:
+            peer = torch.empty(frame_bytes, dtype=torch.uint8, device=dev)
+            whole = ren.frame_params()  # band_count = 1: the unpack kernel degenerates to a row-wise copy
+            rr.ffi.check(lib.rr_bands_unpack_device(C.byref(whole), frame_ptr, frame_bytes, C.c_void_p(peer.data_ptr()), sptr))
         step_gather()
         barrier()
         if rank == 0:
             single = torch.empty(frame_bytes, dtype=torch.uint8, device=dev)
             scene.render_rgb8_device(ren.frame_params(), single.data_ptr(), stream=stream.cuda_stream)
             torch.cuda.synchronize(dev)
-            peer = torch.empty(frame_bytes, dtype=torch.uint8, device=dev)
-            whole = ren.frame_params()  # band_count = 1: the unpack kernel degenerates to a row-wise copy
-            rr.ffi.check(lib.rr_bands_unpack_device(C.byref(whole), frame_ptr, frame_bytes, C.c_void_p(peer.data_ptr()), sptr))
-            torch.cuda.synchronize(dev)
-            ok = bool(torch.equal(peer, single)) and bool(torch.equal(gframe, single))
-            frame_check = "identical to the 1-GPU frame" if ok else "MISMATCH"
+            st = (C.c_uint32 * 1)()
+            rr.ffi.check(lib.rr_device_read(local_rank, status_ptr, st, 4))
+            ok = bool(torch.equal(peer, single)) and bool(torch.equal(gframe, single)) and st[0] == 0
+            frame_check = "identical to the 1-GPU frame" if ok else ("MISMATCH" if st[0] == 0 else "FENCE TIMEOUT")
         barrier()
 
     # ---- e2e: the reference-facing call, frame delivered to page-locked HOST memory ------------
@@ -495,7 +522,7 @@ def main():
         "config": {"workload": name, "width": W, "height": H, "mode": "raymarch" if march else "raytrace",
                    "max_reflections": 3, "max_refractions": 10, "rays_per_frame": rays, "ray_classes": counts,
                    "l2": "flushed between timed steps (256 MiB write, untimed)",
-                   "parallelism": f"row-bands{world}x{BAND_ROWS}, kernel stores rows into rank 0's frame over NVLink (CUDA IPC)"
+                   "parallelism": f"row-bands{world}x{BAND_ROWS}, kernel stores rows AND its completion word into rank 0's memory over NVLink (CUDA IPC), rank 0 waits on the words; no collective"
                    if sharded else "1gpu",
                    "scene_resident": True},
         "frame_ms": ms_per_step,

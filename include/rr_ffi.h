@@ -213,6 +213,22 @@ int rr_render_rgb8_placed_device(rr_scene *scene, const rr_frame_params *params,
                                  size_t row_stride, void *cuda_stream);
 int rr_render_rgb8_placed(rr_scene *scene, const rr_frame_params *params, uint8_t *host_frame,
                           size_t row_stride);
+/* Fused completion for the device frame: no collective after the kernel. The render kernel itself publishes
+ * `epoch` into d_flags[params->band_index] (a uint32 array of band_count words in the FRAME OWNER's memory,
+ * allocated with rr_device_alloc + rr_device_memset(0) and mapped by the other ranks like the frame) once all of
+ * this shard's rows are in the frame: system-scope fence per block, last block does the release store
+ * (ray-march mode: a one-thread publisher queued behind the render). The owner calls rr_fence_wait_device to make
+ * its stream wait until all `count` words have reached `epoch` (acquire loads, bounded by timeout_ms; on timeout
+ * *d_status is set to 1, d_status may be NULL). Epochs must grow from frame to frame. Both calls only enqueue work
+ * (cuda_stream NULL = the default stream); signalled renders of one handle must be ordered on one stream.
+ * This replaces the channel receive loop of render.rs:871-886 across GPUs. */
+int rr_render_rgb8_placed_signal_device(rr_scene *scene, const rr_frame_params *params, void *d_frame,
+                                        size_t row_stride, uint32_t *d_flags, uint32_t epoch,
+                                        void *cuda_stream);
+int rr_fence_wait_device(int device, const uint32_t *d_flags, int32_t count, uint32_t epoch,
+                         uint32_t timeout_ms, uint32_t *d_status, void *cuda_stream);
+int rr_device_memset(int device, void *d_ptr, int value, size_t bytes);
+int rr_device_read(int device, const void *d_ptr, void *host, size_t bytes);
 int rr_device_alloc(int device, size_t bytes, void **d_ptr);
 int rr_device_free(int device, void *d_ptr);
 int rr_ipc_export(void *d_ptr, uint8_t handle[64]);

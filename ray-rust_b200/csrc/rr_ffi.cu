@@ -117,9 +117,15 @@ rr::FrameParams to_dev(const rr_frame_params *p) {
 }
 
 int launch(rr_scene *s, const rr::FrameParams &P, void *d_out, size_t row_stride, bool f32, rr::Counters *d_cnt,
-           cudaStream_t st) {
+           cudaStream_t st, unsigned *d_flag = nullptr, unsigned epoch = 0) {
+    // The trace kernel publishes the completion signal itself (last block); march mode and empty shards fall back to
+    // a one-thread publisher queued behind the render on the same stream.
+    const rr::Signal sig{s->d_work + 8, d_flag, epoch};
+    const bool fused = d_flag && !P.use_raymarching && P.xres > 0 && P.local_rows > 0;
     cudaError_t e = P.use_raymarching ? rr::launch_march(s->G, s->H, P, d_out, row_stride, f32, d_cnt, s->d_work, st, s->li)
-                                      : rr::launch_trace(s->G, s->H, P, d_out, row_stride, f32, d_cnt, st, s->li, s->culling);
+                                      : rr::launch_trace(s->G, s->H, P, d_out, row_stride, f32, d_cnt, st, s->li, s->culling,
+                                                         fused ? sig : rr::Signal{nullptr, nullptr, 0u});
+    if (e == cudaSuccess && d_flag && !fused) e = rr::launch_signal(sig, st);
     if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
     return RR_OK;
 }
@@ -442,6 +448,8 @@ int rr_scene_create(const rr_scene_desc *desc, int device, rr_scene **out) {
         return bail(fail_cuda(e, "rr_scene_create"));
     s->allocs.push_back(s->d_cnt);
     s->allocs.push_back(s->d_work);
+    if ((e = cudaMemset(s->d_work, 0, 64)) != cudaSuccess) return bail(fail_cuda(e, "cudaMemset"));
+    if ((e = rr::preload_signal_kernels()) != cudaSuccess) return bail(fail_cuda(e, "preload"));  // word 8: Signal::done
     for (auto &ev : s->chunk_ev)
         if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
     s->li.sm_count = sm;
@@ -613,6 +621,45 @@ int rr_render_rgb8_placed_device(rr_scene *s, const rr_frame_params *params, voi
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
     s->timed = true;
+    return RR_OK;
+}
+
+// Same render, plus the completion signal carried by the kernel (rr_device.cuh Signal): epoch lands in
+// d_flags[band_index] of the frame owner's memory once every row of this shard is in the frame.
+int rr_render_rgb8_placed_signal_device(rr_scene *s, const rr_frame_params *params, void *d_frame, size_t row_stride,
+                                        uint32_t *d_flags, uint32_t epoch, void *cuda_stream) {
+    if (!s || !d_frame || !d_flags) return fail(RR_ERR_BAD_ARG, "scene/d_frame/d_flags is null");
+    int rc = check_params(params);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->device));
+    rr::FrameParams P = to_dev(params);
+    P.placed = 1;
+    if (row_stride == 0) row_stride = (size_t)P.xres * 3;
+    if (row_stride < (size_t)P.xres * 3) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
+    return launch(s, P, d_frame, row_stride, false, nullptr, reinterpret_cast<cudaStream_t>(cuda_stream), d_flags + P.band_index, epoch);
+}
+
+int rr_fence_wait_device(int device, const uint32_t *d_flags, int32_t count, uint32_t epoch, uint32_t timeout_ms, uint32_t *d_status,
+                         void *cuda_stream) {
+    if (!d_flags || count < 0) return fail(RR_ERR_BAD_ARG, "d_flags is null or count < 0");
+    CU(cudaSetDevice(device));
+    CU(rr::launch_fence_wait(d_flags, count, epoch, timeout_ms, d_status, reinterpret_cast<cudaStream_t>(cuda_stream)));
+    return RR_OK;
+}
+
+int rr_device_memset(int device, void *d_ptr, int value, size_t bytes) {
+    if (!d_ptr) return fail(RR_ERR_BAD_ARG, "d_ptr is null");
+    CU(cudaSetDevice(device));
+    CU(cudaMemset(d_ptr, value, bytes));
+    CU(cudaDeviceSynchronize());
+    return RR_OK;
+}
+
+int rr_device_read(int device, const void *d_ptr, void *host, size_t bytes) {
+    if (!d_ptr || !host) return fail(RR_ERR_BAD_ARG, "d_ptr/host is null");
+    CU(cudaSetDevice(device));
+    CU(cudaMemcpy(host, d_ptr, bytes, cudaMemcpyDeviceToHost));
     return RR_OK;
 }
 

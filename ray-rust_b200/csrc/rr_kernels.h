@@ -17,13 +17,21 @@ struct LaunchInfo {
 // Ray-trace mode. d_out: RGB8 (row_stride bytes per row) or, when f32_out, packed float rgb.
 // d_cnt != nullptr selects the instrumented instantiation.
 cudaError_t launch_trace(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
-                         Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh);
+                         Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh, const Signal &sig = Signal{nullptr, nullptr, 0u});
 // Ray-march mode (same contract). d_work: one unsigned int work counter (zeroed by the launcher).
 cudaError_t launch_march(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
                          Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li);
 // Row-band un-interleave (multi-GPU gather epilogue).
 cudaError_t launch_bands_unpack(const FrameParams &P, const void *d_packed, size_t shard_stride, void *d_frame,
                                 cudaStream_t stream);
+// Completion signalling between GPUs without a collective (see Signal in rr_device.cuh):
+//   launch_signal: stand-alone publisher for kernels that do not carry the signal themselves (march mode);
+//   launch_fence_wait: the frame owner's stream waits until `count` flag words have reached `epoch`
+//   (bounded spin; *d_status = 1 on timeout when d_status is given).
+cudaError_t launch_signal(const Signal &sig, cudaStream_t stream);
+cudaError_t preload_signal_kernels();
+cudaError_t launch_fence_wait(const unsigned *d_flags, int count, unsigned epoch, unsigned timeout_ms, unsigned *d_status,
+                              cudaStream_t stream);
 // FP32 pipe calibration (roofline denominator): achieved TFLOP/s of unfused FMUL+FADD and of FFMA.
 cudaError_t fp32_peak(int device, float *unfused_tflops, float *ffma_tflops);
 

@@ -74,7 +74,7 @@ __device__ __forceinline__ SceneView stage_scene(const DevScene &G, float4 *smem
 template <bool COUNT, bool F32OUT, bool STAGE, bool BVH, int TW>
 __global__ void __launch_bounds__(TRACE_THREADS, RR_TRACE_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHead H, const __grid_constant__ FrameParams P,
-             void *__restrict__ out, size_t row_stride, Counters *gcnt, int fast_store, float inv_tiles_x) {
+             void *__restrict__ out, size_t row_stride, Counters *gcnt, int fast_store, float inv_tiles_x, const Signal sig) {
     extern __shared__ float4 rr_smem[];
     const SceneView S = stage_scene<BVH>(G, rr_smem, STAGE);
 
@@ -126,6 +126,7 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
         }
     }
     if (COUNT) flush_counters(cnt, gcnt);
+    publish_done(sig);
 }
 
 static size_t trace_smem_bytes(const DevScene &G, bool bvh) {
@@ -139,7 +140,7 @@ static size_t trace_smem_bytes(const DevScene &G, bool bvh) {
 
 template <bool COUNT, bool F32OUT, bool STAGE, bool BVH, int TW>
 static cudaError_t launch_tw(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
-                             Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, size_t smem) {
+                             Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, size_t smem, const Signal &sig) {
     auto kern = trace_kernel<COUNT, F32OUT, STAGE, BVH, TW>;
     constexpr int TH = 32 / TW;
     cudaError_t e;
@@ -159,41 +160,41 @@ static cudaError_t launch_tw(const DevScene &G, const SceneHead &H, const FrameP
     if (grid < 1) grid = 1;
     const int fast = (!F32OUT && (P.xres % TW == 0) && (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0)) ? 1 : 0;
     const float inv_tx = tiles < (1 << 24) ? 1.0f / (float)tiles_x : 0.0f;
-    kern<<<(unsigned)grid, TRACE_THREADS, smem, stream>>>(G, H, P, d_out, row_stride, d_cnt, fast, inv_tx);
+    kern<<<(unsigned)grid, TRACE_THREADS, smem, stream>>>(G, H, P, d_out, row_stride, d_cnt, fast, inv_tx, sig);
     return cudaGetLastError();
 }
 
 // Tile shape: 8x4 for local output; 32x1 row tiles when the rows are placed into a (possibly peer) frame.
 template <bool COUNT, bool F32OUT, bool STAGE, bool BVH>
 static cudaError_t launch_one(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
-                              Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, size_t smem) {
+                              Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, size_t smem, const Signal &sig) {
     if constexpr (!F32OUT && !COUNT) {
         if (P.placed && P.xres % 32 == 0)
-            return launch_tw<COUNT, F32OUT, STAGE, BVH, 32>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem);
+            return launch_tw<COUNT, F32OUT, STAGE, BVH, 32>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem, sig);
     }
-    return launch_tw<COUNT, F32OUT, STAGE, BVH, 8>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem);
+    return launch_tw<COUNT, F32OUT, STAGE, BVH, 8>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem, sig);
 }
 
 template <bool COUNT, bool F32OUT>
 static cudaError_t launch_two(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
-                              Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh) {
+                              Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh, const Signal &sig) {
     const bool bvh = allow_bvh && G.n_bvh_nodes > 0;
     size_t smem = trace_smem_bytes(G, bvh);
     const bool stage = smem <= li.smem_optin / 2;  // keep >= 2 blocks per SM resident
     if (!stage) smem = 0;
-    if (bvh) return stage ? launch_one<COUNT, F32OUT, true, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem)
-                          : launch_one<COUNT, F32OUT, false, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem);
-    return stage ? launch_one<COUNT, F32OUT, true, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem)
-                 : launch_one<COUNT, F32OUT, false, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem);
+    if (bvh) return stage ? launch_one<COUNT, F32OUT, true, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem, sig)
+                          : launch_one<COUNT, F32OUT, false, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem, sig);
+    return stage ? launch_one<COUNT, F32OUT, true, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem, sig)
+                 : launch_one<COUNT, F32OUT, false, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem, sig);
 }
 
 cudaError_t launch_trace(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
-                         bool f32_out, Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh) {
+                         bool f32_out, Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh, const Signal &sig) {
     if (P.xres <= 0 || P.local_rows <= 0) return cudaSuccess;
-    if (d_cnt) return f32_out ? launch_two<true, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, allow_bvh)
-                              : launch_two<true, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, allow_bvh);
-    return f32_out ? launch_two<false, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, allow_bvh)
-                   : launch_two<false, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, allow_bvh);
+    if (d_cnt) return f32_out ? launch_two<true, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, allow_bvh, sig)
+                              : launch_two<true, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, allow_bvh, sig);
+    return f32_out ? launch_two<false, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, allow_bvh, sig)
+                   : launch_two<false, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, allow_bvh, sig);
 }
 
 }  // namespace rr

@@ -34,6 +34,58 @@ cudaError_t launch_bands_unpack(const FrameParams &P, const void *d_packed, size
     return cudaGetLastError();
 }
 
+// ---- completion signal / wait (multi-GPU placed frames) ----------------------------------------
+__global__ void signal_kernel(const Signal sig) {
+    // everything earlier on this stream has completed and is visible; publish with system scope
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(sig.flag), "r"(sig.epoch) : "memory");
+}
+
+cudaError_t launch_signal(const Signal &sig, cudaStream_t stream) {
+    if (!sig.flag) return cudaSuccess;
+    signal_kernel<<<1, 1, 0, stream>>>(sig);
+    return cudaGetLastError();
+}
+
+// One thread per flag word. Epochs only grow, so "reached" is a signed distance test (wrap-safe).
+__global__ void fence_wait_kernel(const unsigned *flags, int count, unsigned epoch, unsigned long long timeout_ns, unsigned *status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+        if ((int)(v - epoch) >= 0) break;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) {
+            if (status) atomicExch(status, 1u);
+            break;
+        }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+
+cudaError_t launch_fence_wait(const unsigned *d_flags, int count, unsigned epoch, unsigned timeout_ms, unsigned *d_status,
+                              cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    const int threads = count < 128 ? count : 128;
+    fence_wait_kernel<<<(count + threads - 1) / threads, threads, 0, stream>>>(d_flags, count, epoch,
+                                                                             (unsigned long long)timeout_ms * 1000000ull, d_status);
+    return cudaGetLastError();
+}
+
+// With CUDA's lazy module loading a kernel is loaded at its first launch, which cannot complete while another kernel
+// (a spinning fence_wait_kernel) occupies the device. Load the two signalling kernels up front.
+cudaError_t preload_signal_kernels() {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, signal_kernel);
+    if (e != cudaSuccess) return e;
+    return cudaFuncGetAttributes(&a, fence_wait_kernel);
+}
+
 // ---- FP32 pipe calibration -------------------------------------------------------------------
 // 8 independent dependency chains per thread so the 4-cycle FMA-pipe latency is covered at
 // 16 warps/SMSP. FUSED=false compiles (under -fmad=false) to FMUL+FADD pairs: the instruction mix

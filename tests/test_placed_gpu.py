@@ -63,3 +63,42 @@ def test_device_alloc_and_ipc_export(rr):
     buf = np.zeros(1 << 16, dtype=np.uint8)
     rr.ffi.check(lib.rr_host_register(buf.ctypes.data_as(C.c_void_p), buf.nbytes))
     rr.ffi.check(lib.rr_host_unregister(buf.ctypes.data_as(C.c_void_p)))
+
+
+@pytest.mark.parametrize("n,w,h,march", [(4, 640, 360, False), (3, 96, 70, True), (8, 64, 24, False)])
+def test_placed_signal_and_fence_wait(rr, n, w, h, march):
+    """Fused completion (rr_render_rgb8_placed_signal_device + rr_fence_wait_device): every shard's kernel publishes its
+    epoch word; the owner's stream waits for all of them. One process plays every rank, each on its own stream, with the
+    wait queued FIRST so that it really has to wait for the flags."""
+    import torch
+
+    ren = rr.default_scene(w, h, use_raymarching=march, glow_effect=1.0 if march else None)
+    scene = rr.DeviceScene(ren, 0)
+    lib = scene.lib
+    full = scene.render_rgb8(ren.frame_params())
+    frame = torch.zeros(h * w * 3, dtype=torch.uint8, device="cuda:0")
+    flags = torch.zeros(n + 1, dtype=torch.int32, device="cuda:0")   # n completion words + 1 status word
+    fptr, sptr = C.c_void_p(flags.data_ptr()), C.c_void_p(flags.data_ptr() + 4 * n)
+    owner, worker = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for epoch in (1, 2):
+        frame.zero_()
+        torch.cuda.synchronize()
+        rr.ffi.check(lib.rr_fence_wait_device(0, fptr, n, epoch, 20000, sptr, C.c_void_p(owner.cuda_stream)))
+        with torch.cuda.stream(owner):
+            snapshot = frame.clone()          # ordered behind the wait on the owner's stream only
+        for k in range(n):                    # 8 shards of a 24-row frame: the last two own no rows at all
+            p = ren.frame_params(4, k, n)
+            rr.ffi.check(lib.rr_render_rgb8_placed_signal_device(scene.handle, C.byref(p), C.c_void_p(frame.data_ptr()), 0, fptr, epoch,
+                                                                 C.c_void_p(worker.cuda_stream)))
+        torch.cuda.synchronize()
+        assert flags.cpu().tolist() == [epoch] * n + [0]
+        assert np.array_equal(snapshot.cpu().numpy().reshape(h, w, 3), full)
+    # a missing shard: the wait gives up after its timeout and reports it in the status word
+    rr.ffi.check(lib.rr_fence_wait_device(0, fptr, n, 3, 50, sptr, C.c_void_p(owner.cuda_stream)))
+    torch.cuda.synchronize()
+    assert flags.cpu().tolist()[n] == 1
+    # argument checks
+    p = ren.frame_params(4, 0, n)
+    assert lib.rr_render_rgb8_placed_signal_device(scene.handle, C.byref(p), C.c_void_p(frame.data_ptr()), 0, None, 1, C.c_void_p(worker.cuda_stream)) == rr.ffi.RR_ERR_BAD_ARG
+    scene.close()

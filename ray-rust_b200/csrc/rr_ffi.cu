@@ -432,6 +432,7 @@ int rr_scene_create(const rr_scene_desc *desc, int device, rr_scene **out) {
         }
         s->H.n_glow_head = ng;
     }
+    rr::fill_march_bounds(s->H, std::min((int)sph.size(), rr::RR_HEAD_SPHERES));
     for (int k = 0; k < rr::RR_HEAD_FLOORS && k < (int)flo_o.size(); ++k) {
         s->H.flo_o[k] = flo_o[k]; s->H.flo_n[k] = flo_n[k]; s->H.flo_oi[k] = flo_oi[k];
     }

@@ -9,6 +9,10 @@
 //     strictly above the running minimum (proof in sphere_dist), so its sqrt/sub/max/compare are
 //     skipped without changing a bit of the result. Spheres with a glowing material are always
 //     evaluated when glow is tracked, because the glow minimum needs their distance;
+//   * the same idea one level up: the head spheres carry a bounding sphere (C, R) (SceneHead::grp, built by the host);
+//     when |C - p|^2 > ((best + R) * (1 + 1e-5))^2 none of them can reach the running minimum and the whole unrolled
+//     scan is skipped (proof in distance_estimate). The glow pass skips the sqrt of a glowing sphere whose glow value
+//     provably cannot go below the minimum accumulated so far (proof there);
 //   * one march call site: a per-thread state machine alternates "trace march" and "shadow march",
 //     so the loop body exists once; the glow distance (render.rs:1244-1247) is tracked only for trace
 //     marches and only when --gloweffect is set and a glowing material exists (nothing else reads it);
@@ -83,20 +87,37 @@ __device__ __forceinline__ void sphere_dist(const float4 &c, float glow, int oi,
     }
 }
 
-// distance_estimate, render.rs:1226-1251
+// distance_estimate, render.rs:1226-1251. `glowing` is in/out: the smallest glow value seen so far by the caller
+// (render.rs:1281 takes the minimum over the march, :1331 over the marches of a frame; only that minimum is used).
+//
+// Group skip. The host stores in H.grp a sphere (C, R) with |C - c_s| + r_s <= R for every head sphere s (all r_s >= 0,
+// else R = -1 = disabled). For any p: |c_s - p| - r_s >= |C - p| - R. If the f32 squared distance sqC (same operation
+// order as sphere_dist: relative error <= 5u, u = 2^-24) satisfies sqC > fl(fl(T*T) * 1.00001), T = fl(best + R), then
+// |C - p| =: x > (best + R)(1 + 4.4e-6), and the distance the reference computes for s, fl(fl(sqrt(sq_s)) - r_s), is
+// >= (x - R) - 3.5u (x + R) - u x >= best (1 + 4.1e-6) + 3.9e-6 R > best: no head sphere can lower or tie the running
+// minimum, exactly the situation in which sphere_dist() returns early for each of them. best = inf or NaN never skips.
 template <int GLOW>
 __device__ __forceinline__ void distance_estimate(const SceneHead &H, const MarchView &S, const V3 &vi, int ig, bool track,
                                                   float &closest, int &idx_out, float &glowing) {
-    float best = RR_INF, gl = RR_INF;
+    float best = RR_INF, gl = glowing;
     int idx = 0;
 #pragma unroll
     for (int f = 0; f < RR_HEAD_FLOORS; ++f)
         if (f < S.n_floors) floor_dist<GLOW>(H.flo_o[f], H.flo_n[f], H.flo_oi[f], vi, ig, track, best, idx, gl);
     for (int f = RR_HEAD_FLOORS; f < S.n_floors; ++f)
         floor_dist<GLOW>(S.flo_o[f], S.flo_n[f], S.flo_oi[f], vi, ig, track, best, idx, gl);
+    bool head_far = false;
+    if (H.grp.w >= 0.0f && !(GLOW == 2 && track)) {
+        const V3 d = mk(H.grp.x, H.grp.y, H.grp.z) - vi;
+        const float sq = d.x * d.x + d.y * d.y + d.z * d.z;
+        const float T = best + H.grp.w;
+        head_far = sq > T * T * 1.00001f;
+    }
+    if (!head_far) {
 #pragma unroll
-    for (int s = 0; s < RR_HEAD_SPHERES; ++s)
-        if (s < S.n_spheres) sphere_dist<GLOW>(H.sph_m[s], H.sph_glow[s], H.sph_oi[s], vi, ig, track, best, idx, gl);
+        for (int s = 0; s < RR_HEAD_SPHERES; ++s)
+            if (s < S.n_spheres) sphere_dist<GLOW>(H.sph_m[s], H.sph_glow[s], H.sph_oi[s], vi, ig, track, best, idx, gl);
+    }
 #pragma unroll 2
     for (int s = RR_HEAD_SPHERES; s < S.n_spheres; ++s)
         sphere_dist<GLOW>(S.sph[s], GLOW == 2 ? S.sph_glow[s] : 0.0f, S.sph_oi[s], vi, ig, track, best, idx, gl);
@@ -104,6 +125,10 @@ __device__ __forceinline__ void distance_estimate(const SceneHead &H, const Marc
         // glow pass (render.rs:1244-1247) over the few glowing objects only; their distance is formed
         // with the same operations as in the scan, so the bits are the same whether or not the scan
         // above skipped the object's sqrt.
+        // Sqrt skip: a glowing sphere (r >= 0, k = glow_dist > 0; the host stores glow_ik = fl(1/k), NaN otherwise) can
+        // only lower gl if fl(dist * k) < gl. With T = fl(fl(gl * ik) + r) >= (gl/k + r)(1 - 3u): sq > fl(fl(T*T) * 1.00002)
+        // implies sqrt(sq) >= (gl/k + r)(1 + 9.3e-6), dist >= (gl/k)(1 + 9.2e-6), fl(dist * k) > gl: no update. gl = inf or a
+        // NaN anywhere makes the comparison false and the value is computed.
 #pragma unroll 1
         for (int g = 0; g < H.n_glow_head; ++g) {  // rolled: keeps the march loop inside the L0 I-cache
             if (H.glow_oi[g] != ig) {
@@ -111,7 +136,10 @@ __device__ __forceinline__ void distance_estimate(const SceneHead &H, const Marc
                 float dist;
                 if (H.glow_kind[g] == 0) {
                     const V3 d = mk(a.x, a.y, a.z) - vi;
-                    dist = fmaxf(sqrtf(d.x * d.x + d.y * d.y + d.z * d.z) - a.w, 0.0f);
+                    const float sq = d.x * d.x + d.y * d.y + d.z * d.z;
+                    const float T = gl * H.glow_ik[g] + a.w;
+                    if (sq > T * T * 1.00002f) continue;
+                    dist = fmaxf(sqrtf(sq) - a.w, 0.0f);
                 } else {
                     const float4 nn = H.glow_b[g];
                     dist = fmaxf(dot(vi - mk(a.x, a.y, a.z), mk(nn.x, nn.y, nn.z)), 0.0f);
@@ -126,22 +154,22 @@ __device__ __forceinline__ void distance_estimate(const SceneHead &H, const Marc
     glowing = gl;
 }
 
-// raymarch_single, render.rs:1266-1297
+// raymarch_single, render.rs:1266-1297. `glow_bound`: the smallest glow value the calling frame has seen so far (inf
+// for a fresh frame); the returned min_dist is min(glow_bound, this march's minimum), which is all the caller uses.
 template <int GLOW>
 __device__ __forceinline__ MarchResult raymarch_single(const SceneHead &H, const MarchView &S, const V3 &init_pos,
-                                                       const V3 &eye, int ig, bool track) {
+                                                       const V3 &eye, int ig, bool track, float glow_bound) {
     int iter = 0;
     float travel = 0.0f;
     V3 pos = init_pos;
-    float min_dist = RR_INF;
+    float min_dist = glow_bound;
     for (;;) {
-        float dist, gl;
+        float dist;
         int idx;
-        distance_estimate<GLOW>(H, S, pos, ig, track, dist, idx, gl);
+        distance_estimate<GLOW>(H, S, pos, ig, track, dist, idx, min_dist);
         pos = (eye * dist) + pos;
         travel += dist;
         iter += 1;
-        if (GLOW && gl < min_dist) min_dist = gl;
         if (dist < RAYMARCH_EPS || FAR_AWAY < dist || MAX_ITER < iter) return MarchResult{dist, idx, pos, iter, travel, min_dist};
     }
 }
@@ -196,7 +224,7 @@ __device__ __forceinline__ V3 march_pixel(const DevScene &G, const SceneHead &H,
             ro = pt + (light * F32_EPSILON);  // render.rs:1034
             rd = light; rig = hidx;
         }
-        const MarchResult r = raymarch_single<GLOW>(H, S, ro, rd, rig, !shadow_phase);
+        const MarchResult r = raymarch_single<GLOW>(H, S, ro, rd, rig, !shadow_phase, shadow_phase ? RR_INF : mmd);
         if (COUNT) {
             if (shadow_phase) {
                 cnt.shadow++;

@@ -73,6 +73,7 @@ void flatten(const rr_scene_desc *d, Flat &f) {
         ++ng;
     }
     H.n_glow_head = ng;
+    fill_march_bounds(H, (int)f.sph.size() < RR_HEAD_SPHERES ? (int)f.sph.size() : RR_HEAD_SPHERES);
 }
 
 FrameParams to_dev(const rr_frame_params *p) {

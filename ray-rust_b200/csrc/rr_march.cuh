@@ -106,12 +106,19 @@ __device__ __forceinline__ void distance_estimate(const SceneHead &H, const Marc
         if (f < S.n_floors) floor_dist<GLOW>(H.flo_o[f], H.flo_n[f], H.flo_oi[f], vi, ig, track, best, idx, gl);
     for (int f = RR_HEAD_FLOORS; f < S.n_floors; ++f)
         floor_dist<GLOW>(S.flo_o[f], S.flo_n[f], S.flo_oi[f], vi, ig, track, best, idx, gl);
-    bool head_far = false;
+    // The same sphere also bounds the glowing spheres of the glow pass when the host says so (H.grp_ik = fl(1 / k_min),
+    // k_min the smallest glow_dist, NaN otherwise): with x = |C - p| > (gl / k_min + R)(1 + 9.3e-6) every glowing sphere g
+    // has fl(dist_g * k_g) >= (x - R - 3.5u (x + R) - u x) k_min (1 - u) > gl, so the whole pass cannot lower gl.
+    bool head_far = false, glow_far = false;
     if (H.grp.w >= 0.0f && !(GLOW == 2 && track)) {
         const V3 d = mk(H.grp.x, H.grp.y, H.grp.z) - vi;
         const float sq = d.x * d.x + d.y * d.y + d.z * d.z;
         const float T = best + H.grp.w;
         head_far = sq > T * T * 1.00001f;
+        if (GLOW == 1 && track) {
+            const float Tg = gl * H.grp_ik + H.grp.w;
+            glow_far = sq > Tg * Tg * 1.00002f;
+        }
     }
     if (!head_far) {
 #pragma unroll
@@ -121,7 +128,7 @@ __device__ __forceinline__ void distance_estimate(const SceneHead &H, const Marc
 #pragma unroll 2
     for (int s = RR_HEAD_SPHERES; s < S.n_spheres; ++s)
         sphere_dist<GLOW>(S.sph[s], GLOW == 2 ? S.sph_glow[s] : 0.0f, S.sph_oi[s], vi, ig, track, best, idx, gl);
-    if (GLOW == 1 && track) {
+    if (GLOW == 1 && track && !glow_far) {
         // glow pass (render.rs:1244-1247) over the few glowing objects only; their distance is formed
         // with the same operations as in the scan, so the bits are the same whether or not the scan
         // above skipped the object's sqrt.

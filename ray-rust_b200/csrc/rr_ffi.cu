@@ -269,6 +269,23 @@ int pick_chunks(size_t bytes, const rr::FrameParams &P, const rr_scene *s) {
     return (int)n;
 }
 
+// Long kernels (the same predicate for which chunking does not pay): when the caller's frame is page-locked, mapped host
+// memory (rr_host_alloc, rr_host_register, cudaHostAlloc), the kernel stores its RGB8 tiles straight into it over PCIe.
+// The copy disappears behind the kernel: at >= 2.7 ms per 24.9 MB frame the stores need < 10 GB/s of the link
+// (profiles/r1_s2_zero_copy.md: config 4 e2e 3.23 -> 2.80 ms, config 3 8.14 -> 7.78 ms). Short kernels keep the chunked
+// device-buffer + DMA pipeline: 24-byte tile rows reach only 18 GB/s as PCIe writes.
+bool long_kernel(const rr::FrameParams &P, const rr_scene *s) { return P.use_raymarching || s->G.n_objects > 64; }
+
+bool mapped_host_alias(const void *host, size_t row_stride, void **dev) {
+    static const bool enabled = [] { const char *e = getenv("RR_E2E_ZERO_COPY"); return e ? atoi(e) != 0 : true; }();
+    if (!enabled || (row_stride & 3) || (reinterpret_cast<uintptr_t>(host) & 3)) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+    *dev = a.devicePointer;
+    return true;
+}
+
 int ensure_out(rr_scene *s, size_t bytes) {
     if (bytes <= s->d_out_cap) return RR_OK;
     if (s->d_out) cudaFree(s->d_out);
@@ -518,6 +535,16 @@ int rr_render_rgb8(rr_scene *s, const rr_frame_params *params, uint8_t *out, siz
     if (row_stride < packed) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
     const int rows = P.local_rows;
     if (rows == 0 || P.xres == 0) return RR_OK;
+    void *alias = nullptr;
+    if (long_kernel(P, s) && P.xres % 8 == 0 && mapped_host_alias(out, row_stride, &alias)) {
+        CU(cudaEventRecord(s->ev0, s->stream));
+        if ((rc = launch(s, P, alias, row_stride, false, nullptr, s->stream))) return rc;
+        CU(cudaEventRecord(s->ev1, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+        s->timed = true;
+        return RR_OK;
+    }
     if ((rc = ensure_out(s, packed * rows))) return rc;
     const int nchunk = pick_chunks(packed * rows, P, s);
     int chunk_rows = (rows + nchunk - 1) / nchunk;
@@ -678,6 +705,18 @@ int rr_render_rgb8_placed(rr_scene *s, const rr_frame_params *params, uint8_t *h
     if (row_stride < packed) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
     const int rows = P.local_rows;
     if (rows == 0 || P.xres == 0) return RR_OK;
+    void *alias = nullptr;
+    if (long_kernel(P, s) && P.xres % 8 == 0 && mapped_host_alias(host_frame, row_stride, &alias)) {
+        rr::FrameParams Z = P;
+        Z.placed = 1;  // rows go to their image position in the (shared) host frame
+        CU(cudaEventRecord(s->ev0, s->stream));
+        if ((rc = launch(s, Z, alias, row_stride, false, nullptr, s->stream))) return rc;
+        CU(cudaEventRecord(s->ev1, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+        s->timed = true;
+        return RR_OK;
+    }
     if ((rc = ensure_out(s, packed * rows))) return rc;
     const int B = P.band_count <= 1 ? 4 : P.band_rows, n = P.band_count, k = P.band_index;
     // Same pipeline as rr_render_rgb8: up to 8 chunks of whole bands, each chunk's device-to-host copy

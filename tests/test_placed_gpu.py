@@ -102,3 +102,34 @@ def test_placed_signal_and_fence_wait(rr, n, w, h, march):
     p = ren.frame_params(4, 0, n)
     assert lib.rr_render_rgb8_placed_signal_device(scene.handle, C.byref(p), C.c_void_p(frame.data_ptr()), 0, None, 1, C.c_void_p(worker.cuda_stream)) == rr.ffi.RR_ERR_BAD_ARG
     scene.close()
+
+
+@pytest.mark.parametrize("kind", ["march", "synthetic"])
+def test_zero_copy_pinned_host_frame(rr, kind):
+    """Long kernels store straight into a page-locked host frame (no device buffer, no DMA copy); the bytes must equal
+    the pageable-buffer path, for packed and padded rows, whole frames and row-band shards placed into one frame."""
+    w, h = 256, 144
+    ren = (rr.default_scene(w, h, use_raymarching=True, glow_effect=1.0) if kind == "march"
+           else rr.synthetic_scene(w, h, n_spheres=100))
+    scene = rr.DeviceScene(ren, 0)
+    lib = scene.lib
+    p = ren.frame_params()
+    pageable = scene.render_rgb8(p)                       # numpy buffer: device buffer + cudaMemcpy
+    stride = w * 3 + 16
+    host = C.c_void_p()
+    rr.ffi.check(lib.rr_host_alloc(stride * h, C.byref(host)))
+    pinned = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_uint8)), shape=(h, stride))
+    pinned[:] = 0xCD
+    rr.ffi.check(lib.rr_render_rgb8(scene.handle, C.byref(p), host, 0))
+    assert np.array_equal(pinned.reshape(-1)[: h * w * 3].reshape(h, w, 3), pageable)
+    pinned[:] = 0xCD
+    rr.ffi.check(lib.rr_render_rgb8(scene.handle, C.byref(p), host, stride))
+    assert np.array_equal(pinned[:, : w * 3].reshape(h, w, 3), pageable) and (pinned[:, w * 3:] == 0xCD).all()
+    pinned[:] = 0xCD
+    for k in range(3):
+        pk = ren.frame_params(16, k, 3)
+        rr.ffi.check(lib.rr_render_rgb8_placed(scene.handle, C.byref(pk), host, stride))
+    assert np.array_equal(pinned[:, : w * 3].reshape(h, w, 3), pageable) and (pinned[:, w * 3:] == 0xCD).all()
+    del pinned
+    lib.rr_host_free(host)
+    scene.close()

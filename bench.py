@@ -484,18 +484,31 @@ def main():
                 "peak_gbs": hbm_peak, "frac": fb_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
     }
-    if not march and ren.flatten().desc.n_objects >= 25:
-        # the exact BVH cull skips most of the reference's brute-force tests: the algorithmic (reference-
-        # equivalent) flop rate then says nothing about pipe utilisation and must not be read as a roofline fraction
-        roofline["frac_reference_equivalent"] = roofline["frac"]
-        roofline["frac"] = None
-        roofline["note"] = "BVH-culled launch: achieved = reference-equivalent flops / time; executed flops are far fewer"
+    prof = {}
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        roofline["traffic"] = prof.get(name, {}).get("dram_bytes_per_launch")
-        roofline["traffic_note"] = prof.get(name, {}).get("note")
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name, {})
     except Exception:
         pass
+    roofline["traffic"] = prof.get("dram_bytes_per_launch")
+    roofline["traffic_note"] = prof.get("note")
+    culled = march or ren.flatten().desc.n_objects >= 25
+    if culled:
+        # The exact culls (BVH; in march mode the sqrt / bounding-sphere / glow skips) remove most of the reference's
+        # brute-force arithmetic, so reference-equivalent flops / time says nothing about pipe utilisation and must not be
+        # read as a roofline fraction. frac is computed from the flops the kernel EXECUTES (ncu count of the same launch,
+        # committed under profiles/), the reference-equivalent rate is kept beside it.
+        roofline["frac_reference_equivalent"] = roofline["frac"]
+        roofline["achieved_reference_equivalent"] = roofline["achieved"]
+        ex = prof.get("executed_flops_per_launch") if not sharded and (W, H) == (3840, 2160) else None
+        roofline["achieved"] = ex / (kernel_ms * 1e-3) / 1e12 if ex else None
+        roofline["frac"] = roofline["achieved"] / derived_unfused if ex else None
+        roofline["frac_of_measured_unfused"] = roofline["achieved"] / a.value if ex and a.value else None
+        roofline["executed_flops_per_launch"] = ex
+        roofline["note"] = ("culled launch: achieved/frac = flops EXECUTED per launch (ncu, " + str(prof.get("executed_note")) +
+                            ") / live kernel time; *_reference_equivalent = the reference's brute-force flop count / the same time")
+    elif prof.get("executed_flops_per_launch") and not sharded and (W, H) == (3840, 2160):
+        roofline["executed_flops_per_launch"] = prof["executed_flops_per_launch"]
+        roofline["frac_executed"] = prof["executed_flops_per_launch"] / (kernel_ms * 1e-3) / 1e12 / derived_unfused
 
     # ---- CPU baseline beside it (oracle port on all host cores; bounded sample) -----------------
     cpu = None

@@ -269,6 +269,34 @@ int pick_chunks(size_t bytes, const rr::FrameParams &P, const rr_scene *s) {
     return (int)n;
 }
 
+// Row counts of the chunks (whole 4-row tiles): a geometric plan. The first chunk is rows/d, so that the first copy starts
+// after ~1/48 of the kernel work, every next one g times larger, so that the copy engine sees ~9 copies instead of 16
+// (a ~1.5 us gap each) while kernel k+1 (g x the rows at ~100 GB/s-equivalent) still ends before copy k (56 GB/s) does.
+// Measured against the uniform 16 x 1.5 MB plan (tools/ab_e2e_geom.py): 4K 0.523-0.531 -> 0.496-0.498 ms, 8K 1.88-1.92 ->
+// 1.86 ms; g = 2 is slower (the kernel falls behind the copy). RR_E2E_GEOM="d,g" overrides, "0" selects the uniform plan.
+int plan_chunks(int rows, int nchunk, int *plan) {
+    static const double geom_d = [] { const char *e = getenv("RR_E2E_GEOM"); return e ? atof(e) : 48.0; }();
+    static const double geom_g = [] { const char *e = getenv("RR_E2E_GEOM"); const char *c = e ? strchr(e, ',') : nullptr; return c ? atof(c + 1) : 1.5; }();
+    int n = 0, done = 0;
+    if (geom_d >= 2.0 && nchunk > 1) {
+        double want = rows / geom_d;
+        while (done < rows && n < 31) {
+            int r = ((int)want + 3) & ~3;
+            if (r < 4) r = 4;
+            if (r > rows - done) r = rows - done;
+            plan[n++] = r;
+            done += r;
+            want *= geom_g;
+        }
+        if (done < rows) plan[n++] = rows - done;
+        return n;
+    }
+    int chunk_rows = (rows + nchunk - 1) / nchunk;
+    chunk_rows = (chunk_rows + 3) & ~3;
+    for (; done < rows; done += chunk_rows) plan[n++] = rows - done < chunk_rows ? rows - done : chunk_rows;
+    return n;
+}
+
 // Long kernels (the same predicate for which chunking does not pay): when the caller's frame is page-locked, mapped host
 // memory (rr_host_alloc, rr_host_register, cudaHostAlloc), the kernel stores its RGB8 tiles straight into it over PCIe.
 // The copy disappears behind the kernel: at >= 2.7 ms per 24.9 MB frame the stores need < 10 GB/s of the link
@@ -547,14 +575,13 @@ int rr_render_rgb8(rr_scene *s, const rr_frame_params *params, uint8_t *out, siz
     }
     if ((rc = ensure_out(s, packed * rows))) return rc;
     const int nchunk = pick_chunks(packed * rows, P, s);
-    int chunk_rows = (rows + nchunk - 1) / nchunk;
-    chunk_rows = (chunk_rows + 3) & ~3;  // whole 4-row tiles
+    int plan[32];
+    const int nplan = plan_chunks(rows, nchunk, plan);
     CU(cudaEventRecord(s->ev0, s->stream));
-    int k = 0;
-    for (int r0 = 0; r0 < rows; r0 += chunk_rows, ++k) {
+    for (int k = 0, r0 = 0; k < nplan; r0 += plan[k], ++k) {
         rr::FrameParams C = P;
         C.row0 = r0;
-        C.local_rows = (rows - r0 < chunk_rows) ? rows - r0 : chunk_rows;
+        C.local_rows = plan[k];
         uint8_t *d = reinterpret_cast<uint8_t *>(s->d_out) + (size_t)r0 * packed;
         if ((rc = launch(s, C, d, packed, false, nullptr, s->stream))) return rc;
         CU(cudaEventRecord(s->chunk_ev[k], s->stream));

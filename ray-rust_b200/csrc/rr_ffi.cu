@@ -53,7 +53,8 @@ struct rr_scene {
     void *d_out = nullptr;
     size_t d_out_cap = 0;
     rr::Counters *d_cnt = nullptr;
-    unsigned *d_work = nullptr;
+    unsigned *d_work = nullptr;  // word 0: march tile queue; words 16..79: 16 (work, done, -, -) slots of the trace kernel
+    unsigned launch_seq = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t chunk_ev[32] = {};
     float last_ms = 0.0f;
@@ -118,13 +119,15 @@ rr::FrameParams to_dev(const rr_frame_params *p) {
 
 int launch(rr_scene *s, const rr::FrameParams &P, void *d_out, size_t row_stride, bool f32, rr::Counters *d_cnt,
            cudaStream_t st, unsigned *d_flag = nullptr, unsigned epoch = 0) {
-    // The trace kernel publishes the completion signal itself (last block); march mode and empty shards fall back to
-    // a one-thread publisher queued behind the render on the same stream.
-    const rr::Signal sig{s->d_work + 8, d_flag, epoch};
+    // Each launch takes the next of 16 slots of (work, done) words: the trace kernel's tile queue and block counter reset
+    // themselves at the end of the launch, and kernels of one handle running concurrently on different streams never
+    // share a slot (unless more than 16 overlap). The trace kernel also publishes the completion signal itself (last
+    // block); march mode and empty shards fall back to a one-thread publisher queued behind the render on the same stream.
+    unsigned *slot = s->d_work + 16 + 4 * (s->launch_seq++ & 15u);
+    const rr::Signal sig{slot, slot + 1, d_flag, epoch};
     const bool fused = d_flag && !P.use_raymarching && P.xres > 0 && P.local_rows > 0;
     cudaError_t e = P.use_raymarching ? rr::launch_march(s->G, s->H, P, d_out, row_stride, f32, d_cnt, s->d_work, st, s->li)
-                                      : rr::launch_trace(s->G, s->H, P, d_out, row_stride, f32, d_cnt, st, s->li, s->culling,
-                                                         fused ? sig : rr::Signal{nullptr, nullptr, 0u});
+                                      : rr::launch_trace(s->G, s->H, P, d_out, row_stride, f32, d_cnt, st, s->li, s->culling, sig);
     if (e == cudaSuccess && d_flag && !fused) e = rr::launch_signal(sig, st);
     if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
     return RR_OK;
@@ -490,12 +493,12 @@ int rr_scene_create(const rr_scene_desc *desc, int device, rr_scene **out) {
         (e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&s->ev0)) != cudaSuccess || (e = cudaEventCreate(&s->ev1)) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void **>(&s->d_cnt), sizeof(rr::Counters))) != cudaSuccess ||
-        (e = cudaMalloc(reinterpret_cast<void **>(&s->d_work), 64)) != cudaSuccess)
+        (e = cudaMalloc(reinterpret_cast<void **>(&s->d_work), 512)) != cudaSuccess)
         return bail(fail_cuda(e, "rr_scene_create"));
     s->allocs.push_back(s->d_cnt);
     s->allocs.push_back(s->d_work);
     if ((e = cudaMemset(s->d_work, 0, 64)) != cudaSuccess) return bail(fail_cuda(e, "cudaMemset"));
-    if ((e = rr::preload_signal_kernels()) != cudaSuccess) return bail(fail_cuda(e, "preload"));  // word 8: Signal::done
+    if ((e = rr::preload_signal_kernels()) != cudaSuccess) return bail(fail_cuda(e, "preload"));
     for (auto &ev : s->chunk_ev)
         if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
     s->li.sm_count = sm;

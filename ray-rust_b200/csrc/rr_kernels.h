@@ -17,7 +17,7 @@ struct LaunchInfo {
 // Ray-trace mode. d_out: RGB8 (row_stride bytes per row) or, when f32_out, packed float rgb.
 // d_cnt != nullptr selects the instrumented instantiation.
 cudaError_t launch_trace(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
-                         Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh, const Signal &sig = Signal{nullptr, nullptr, 0u});
+                         Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh, const Signal &sig = Signal{nullptr, nullptr, nullptr, 0u});
 // Ray-march mode (same contract). d_work: one unsigned int work counter (zeroed by the launcher).
 cudaError_t launch_march(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
                          Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li);

@@ -89,44 +89,57 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
     const int nw = gridDim.x * warps_per_block;
     Counters cnt = {};
 
-#ifdef RR_TRACE_PHASE_LOCK
-    // experiment: keep the warps of a block in phase (shared L0/L1.5 instruction fetches)
-    const int iters = (ntiles + nw - 1) / nw;
-    for (int it = 0, tile = gw; it < iters; ++it, tile += nw) {
-        __syncthreads();
-        if (tile >= ntiles) continue;
-#else
-    for (int tile = gw; tile < ntiles; tile += nw) {
-#endif
-        // ty = tile / tiles_x without an integer division: float estimate + one-step correction
-        // (exact for tile < 2^24; the launcher falls back to inv_tiles_x = 0 -> integer division above that)
-        int ty;
-        if (inv_tiles_x > 0.0f) {
-            ty = (int)(((float)tile + 0.5f) * inv_tiles_x);
-            const int r = tile - ty * tiles_x;
-            ty += (r >= tiles_x) ? 1 : ((r < 0) ? -1 : 0);
-        } else {
-            ty = tile / tiles_x;
+    // Tile schedule: static interleaved stride for the first part of the tile list (each warp samples the whole image, so
+    // the correlated cost of neighbouring tiles — sky, floor, glass — is spread over all SMs), then a global queue hands
+    // out the rest one tile at a time (same-address atomics: ~2 G/s on this part, a 4K frame has 259 k tiles). Tile
+    // cost varies by 10x and more; with the static stride alone the busiest SM sub-partition ended ~15 % after the average
+    // one (ncu: 41.7 % warps active of a possible 50 %). Measured static share, kernel ms at 4K default / 8K default /
+    // 4K 1 024 spheres (profiles/r1_s2_tile_schedule.md): 16/16 0.249 / 0.955 / 2.78, 13/16 0.239 / 0.910 / 2.71,
+    // 8/16 0.225 / 0.862 / 2.35, 6/16 0.225 / 0.864 / 2.06, 0/16 0.234 / 0.892 / 2.05. Contiguous chunks per warp
+    // (guided self-scheduling) lose badly (0.35 / 1.28 / 4.0): neighbouring tiles cost alike.
+    constexpr int STATIC_16THS = BVH ? 6 : 8;
+    const int n_static = sig.work ? (int)(((long long)ntiles * STATIC_16THS) >> 4) : ntiles;
+    int nt = gw;
+    for (;;) {
+        if (sig.work && nt >= n_static) {  // warp-uniform: the static share is done (queue tiles are >= n_static, so it stays done)
+            nt = 0;
+            if (lane == 0) nt = n_static + (int)atomicAdd(sig.work, 1u);
+            nt = __shfl_sync(0xffffffffu, nt, 0);
         }
-        const int tx = tile - ty * tiles_x;
-        const int x0 = tx * TW, ly0 = ty * TH;
-        const int ix = x0 + col, ly = ly0 + row;
-        const bool valid = ix < W && ly < rows;
-        V3 c = mk(0.0f, 0.0f, 0.0f);
-        if (valid) c = trace_pixel<COUNT, BVH>(G, H, S, P, ix, local_to_image_row(P, ly), cnt);
-        if (F32OUT) {
-            if (valid) {
-                float *o = reinterpret_cast<float *>(out) + ((size_t)(P.placed ? local_to_image_row(P, ly) : ly) * W + ix) * 3;
-                o[0] = c.x; o[1] = c.y; o[2] = c.z;
+        if (nt >= ntiles) break;
+        const int tile = nt;
+        nt = tile + nw;
+        {
+            // ty = tile / tiles_x without an integer division: float estimate + one-step correction
+            // (exact for tile < 2^24; the launcher falls back to inv_tiles_x = 0 -> integer division above that)
+            int ty;
+            if (inv_tiles_x > 0.0f) {
+                ty = (int)(((float)tile + 0.5f) * inv_tiles_x);
+                const int r = tile - ty * tiles_x;
+                ty += (r >= tiles_x) ? 1 : ((r < 0) ? -1 : 0);
+            } else {
+                ty = tile / tiles_x;
             }
-        } else {
-            const unsigned rgb = quantize(c.x) | (quantize(c.y) << 8) | (quantize(c.z) << 16);
-            store_tile_rgb8<TW>(reinterpret_cast<uint8_t *>(out), row_stride, x0, ly0, W, rows, rgb, fast_store != 0,
-                                P.placed ? local_to_image_row(P, ly) : ly);
+            const int tx = tile - ty * tiles_x;
+            const int x0 = tx * TW, ly0 = ty * TH;
+            const int ix = x0 + col, ly = ly0 + row;
+            const bool valid = ix < W && ly < rows;
+            V3 c = mk(0.0f, 0.0f, 0.0f);
+            if (valid) c = trace_pixel<COUNT, BVH>(G, H, S, P, ix, local_to_image_row(P, ly), cnt);
+            if (F32OUT) {
+                if (valid) {
+                    float *o = reinterpret_cast<float *>(out) + ((size_t)(P.placed ? local_to_image_row(P, ly) : ly) * W + ix) * 3;
+                    o[0] = c.x; o[1] = c.y; o[2] = c.z;
+                }
+            } else {
+                const unsigned rgb = quantize(c.x) | (quantize(c.y) << 8) | (quantize(c.z) << 16);
+                store_tile_rgb8<TW>(reinterpret_cast<uint8_t *>(out), row_stride, x0, ly0, W, rows, rgb, fast_store != 0,
+                                    P.placed ? local_to_image_row(P, ly) : ly);
+            }
         }
     }
     if (COUNT) flush_counters(cnt, gcnt);
-    publish_done(sig);
+    finish_launch(sig);
 }
 
 static size_t trace_smem_bytes(const DevScene &G, bool bvh) {

@@ -266,9 +266,23 @@ def main():
         if rank != 0:
             hb = (C.c_uint8 * 64).from_buffer_copy(box[0])
             rr.ffi.check(lib.rr_ipc_open(local_rank, hb, C.byref(frame_ptr)))
-        flags_ptr = C.c_void_p(frame_ptr.value + flags_off)
-        status_ptr = C.c_void_p(frame_ptr.value + flags_off + 256)
+        flags_ptr = C.c_void_p(frame_ptr.value + flags_off)            # completion words, one per rank
+        status_ptr = C.c_void_p(frame_ptr.value + flags_off + 256)   # timeout status of the wait kernels
+        arrive_ptr = C.c_void_p(frame_ptr.value + flags_off + 128)   # device-side barrier: arrival words, one per rank
+        go_ptr = C.c_void_p(frame_ptr.value + flags_off + 192)       # ... and the release word
         epoch = [0]
+        gate = [0]
+
+        def device_barrier():
+            """Aligns the ranks' streams on the device (flag words in rank 0's memory, written and polled over NVLink):
+            every rank publishes its arrival, rank 0 waits for all of them and opens the gate, every rank waits for the
+            gate. A NCCL barrier lets the ranks' streams resume tens of microseconds apart; this one a few. Untimed."""
+            gate[0] += 1
+            rr.ffi.check(lib.rr_fence_signal_device(local_rank, C.c_void_p(arrive_ptr.value + 4 * rank), gate[0], sptr))
+            if rank == 0:
+                rr.ffi.check(lib.rr_fence_wait_device(local_rank, arrive_ptr, world, gate[0], 5000, status_ptr, sptr))
+                rr.ffi.check(lib.rr_fence_signal_device(local_rank, go_ptr, gate[0], sptr))
+            rr.ffi.check(lib.rr_fence_wait_device(local_rank, go_ptr, 1, gate[0], 5000, status_ptr, sptr))
         tok = torch.zeros(1, dtype=torch.float32, device=dev)
         packed = torch.empty(shard_bytes, dtype=torch.uint8, device=dev)
         gathered = torch.empty(world * shard_bytes, dtype=torch.uint8, device=dev) if rank == 0 else None
@@ -320,6 +334,7 @@ def main():
             flush.fill_(i & 0xFF)  # evict the previous frame from L2 (not timed)
             if dist is not None:
                 dist.barrier()
+                device_barrier()
             ev[i][0].record(stream)
             launches += step_fn()
             ev[i][1].record(stream)

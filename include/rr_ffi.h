@@ -227,6 +227,10 @@ int rr_render_rgb8_placed_signal_device(rr_scene *scene, const rr_frame_params *
                                         void *cuda_stream);
 int rr_fence_wait_device(int device, const uint32_t *d_flags, int32_t count, uint32_t epoch,
                          uint32_t timeout_ms, uint32_t *d_status, void *cuda_stream);
+/* Stand-alone publisher: once everything queued earlier on `cuda_stream` has completed, store `epoch` into *d_flag
+ * (device or peer memory) with system-scope release semantics. With rr_fence_wait_device this builds device-side
+ * barriers / doorbells between the GPUs of one box (bench.py aligns the ranks' frame starts with it). */
+int rr_fence_signal_device(int device, uint32_t *d_flag, uint32_t epoch, void *cuda_stream);
 int rr_device_memset(int device, void *d_ptr, int value, size_t bytes);
 int rr_device_read(int device, const void *d_ptr, void *host, size_t bytes);
 int rr_device_alloc(int device, size_t bytes, void **d_ptr);

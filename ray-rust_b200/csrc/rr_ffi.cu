@@ -706,6 +706,13 @@ int rr_fence_wait_device(int device, const uint32_t *d_flags, int32_t count, uin
     return RR_OK;
 }
 
+int rr_fence_signal_device(int device, uint32_t *d_flag, uint32_t epoch, void *cuda_stream) {
+    if (!d_flag) return fail(RR_ERR_BAD_ARG, "d_flag is null");
+    CU(cudaSetDevice(device));
+    CU(rr::launch_signal(rr::Signal{nullptr, nullptr, d_flag, epoch}, reinterpret_cast<cudaStream_t>(cuda_stream)));
+    return RR_OK;
+}
+
 int rr_device_memset(int device, void *d_ptr, int value, size_t bytes) {
     if (!d_ptr) return fail(RR_ERR_BAD_ARG, "d_ptr is null");
     CU(cudaSetDevice(device));

@@ -78,12 +78,19 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
     extern __shared__ float4 rr_smem[];
     const SceneView S = stage_scene<BVH>(G, rr_smem, STAGE);
 
-    constexpr int TH = 32 / TW;  // warp tile: TW x TH pixels (8x4, or 32x1 for placed output over NVLink)
+    // warp tile: TW x TH pixels. 8x4 (best ray coherence); 32x1 for placed output (one 96-byte run per store); 128x1 =
+    // four 32x1 sub-tiles rendered one after the other and stored together as ONE 384-byte run (three full 128-byte
+    // lines, 16 bytes per lane) for frames that live in a peer GPU's memory: the owner's NVLink ingress is what bounds
+    // the 8-GPU frame, and full-line writes use it best.
+    constexpr int SUB = TW == 128 ? 4 : 1;  // sub-tiles per tile
+    constexpr int TWS = TW / SUB;           // sub-tile width
+    constexpr int TH = 32 / TWS;
+    __shared__ uint4 rr_wbuf[TW == 128 ? TRACE_THREADS / 32 : 1][24];
     const int W = P.xres, rows = P.local_rows;
     const int tiles_x = (W + TW - 1) / TW, tiles_y = (rows + TH - 1) / TH;
     const int ntiles = tiles_x * tiles_y;
     const int lane = threadIdx.x & 31;
-    const int col = lane % TW, row = lane / TW;
+    const int col = lane % TWS, row = lane / TWS;
     const int warps_per_block = blockDim.x >> 5;
     const int gw = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     const int nw = gridDim.x * warps_per_block;
@@ -122,6 +129,28 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
             }
             const int tx = tile - ty * tiles_x;
             const int x0 = tx * TW, ly0 = ty * TH;
+            if constexpr (TW == 128) {
+                // launcher guarantees: RGB8, W % 128 == 0, 16-byte aligned rows (so every lane's uint4 is aligned)
+                const int ly = ly0;
+                const int orow = P.placed ? local_to_image_row(P, ly) : ly;
+                unsigned *wb = reinterpret_cast<unsigned *>(rr_wbuf[threadIdx.x >> 5]);
+#pragma unroll 1
+                for (int sub = 0; sub < SUB; ++sub) {
+                    const V3 c = trace_pixel<COUNT, BVH>(G, H, S, P, x0 + sub * 32 + lane, local_to_image_row(P, ly), cnt);
+                    const unsigned rgb = quantize(c.x) | (quantize(c.y) << 8) | (quantize(c.z) << 16);
+                    // word w of the 96-byte sub-run holds bytes 4w..4w+3 = pixels pa (and pa+1); lanes 0..23 own one word
+                    const int pa = (4 * lane) / 3;
+                    const unsigned va = __shfl_sync(0xffffffffu, rgb, min(pa, 31));
+                    const unsigned vb = __shfl_sync(0xffffffffu, rgb, min(pa + 1, 31));
+                    const unsigned long long both = (unsigned long long)va | ((unsigned long long)vb << 24);
+                    if (lane < 24) wb[sub * 24 + lane] = (unsigned)(both >> (8 * ((4 * lane - 3 * pa) & 3)));
+                }
+                __syncwarp();
+                if (lane < 24)
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(out) + (size_t)orow * row_stride + (size_t)x0 * 3 + 16 * lane) =
+                        rr_wbuf[threadIdx.x >> 5][lane];
+                __syncwarp();
+            } else {
             const int ix = x0 + col, ly = ly0 + row;
             const bool valid = ix < W && ly < rows;
             V3 c = mk(0.0f, 0.0f, 0.0f);
@@ -133,8 +162,9 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
                 }
             } else {
                 const unsigned rgb = quantize(c.x) | (quantize(c.y) << 8) | (quantize(c.z) << 16);
-                store_tile_rgb8<TW>(reinterpret_cast<uint8_t *>(out), row_stride, x0, ly0, W, rows, rgb, fast_store != 0,
-                                    P.placed ? local_to_image_row(P, ly) : ly);
+                store_tile_rgb8<TWS>(reinterpret_cast<uint8_t *>(out), row_stride, x0, ly0, W, rows, rgb, fast_store != 0,
+                                     P.placed ? local_to_image_row(P, ly) : ly);
+            }
             }
         }
     }
@@ -155,7 +185,7 @@ template <bool COUNT, bool F32OUT, bool STAGE, bool BVH, int TW>
 static cudaError_t launch_tw(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
                              Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, size_t smem, const Signal &sig) {
     auto kern = trace_kernel<COUNT, F32OUT, STAGE, BVH, TW>;
-    constexpr int TH = 32 / TW;
+    constexpr int TH = TW == 128 ? 1 : 32 / TW;
     cudaError_t e;
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -177,11 +207,21 @@ static cudaError_t launch_tw(const DevScene &G, const SceneHead &H, const FrameP
     return cudaGetLastError();
 }
 
-// Tile shape: 8x4 for local output; 32x1 row tiles when the rows are placed into a (possibly peer) frame.
+// Tile shape (measured, profiles/r1_s2_tile_schedule.md): 128x1 macro tiles (four 32x1 sub-tiles, one 384-byte store)
+// whenever the frame allows it — they win locally too (4K 0.226 -> 0.217 ms, 8K 0.862 -> 0.807 ms: a quarter of the tile
+// bookkeeping and queue traffic, full-line stores) — except for the BVH instance rendering into local memory, whose
+// incoherent secondary rays want the 8x4 footprint; 32x1 row tiles for other placed frames; 8x4 otherwise.
 template <bool COUNT, bool F32OUT, bool STAGE, bool BVH>
 static cudaError_t launch_one(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
                               Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, size_t smem, const Signal &sig) {
     if constexpr (!F32OUT && !COUNT) {
+        static const bool wide = [] { const char *e = getenv("RR_WIDE_TILES"); return e ? atoi(e) != 0 : true; }();
+        // ... and only when there are enough of them to keep every resident warp busy (>= 4 per warp): the small chunk
+        // launches of the host pipeline (rr_render_rgb8) need the finer 8x4 granularity
+        const long long macro_tiles = (long long)(P.xres / 128) * P.local_rows;
+        const bool enough = macro_tiles >= 4ll * li.sm_count * (RR_TRACE_MIN_BLOCKS * TRACE_THREADS / 32);
+        if (wide && enough && (P.placed || !BVH) && P.xres % 128 == 0 && row_stride % 16 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0)
+            return launch_tw<COUNT, F32OUT, STAGE, BVH, 128>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem, sig);
         if (P.placed && P.xres % 32 == 0)
             return launch_tw<COUNT, F32OUT, STAGE, BVH, 32>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem, sig);
     }

@@ -130,6 +130,7 @@ PROTOTYPES = {
     "rr_render_rgb8_placed": (C.c_int, [_P, C.POINTER(rr_frame_params), _P, C.c_size_t]),
     "rr_render_rgb8_placed_signal_device": (C.c_int, [_P, C.POINTER(rr_frame_params), _P, C.c_size_t, _P, C.c_uint32, _P]),
     "rr_fence_wait_device": (C.c_int, [C.c_int, _P, C.c_int32, C.c_uint32, C.c_uint32, _P, _P]),
+    "rr_fence_signal_device": (C.c_int, [C.c_int, _P, C.c_uint32, _P]),
     "rr_device_memset": (C.c_int, [C.c_int, _P, C.c_int, C.c_size_t]),
     "rr_device_read": (C.c_int, [C.c_int, _P, _P, C.c_size_t]),
     "rr_device_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_P)]),

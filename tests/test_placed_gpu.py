@@ -133,3 +133,28 @@ def test_zero_copy_pinned_host_frame(rr, kind):
     del pinned
     lib.rr_host_free(host)
     scene.close()
+
+
+def test_fence_signal_memset_read(rr):
+    """The stand-alone publisher + wait pair (device-side barrier / doorbell primitive) and the raw device helpers."""
+    import torch
+
+    lib = rr.ffi.load()
+    p = C.c_void_p()
+    rr.ffi.check(lib.rr_device_alloc(0, 256, C.byref(p)))
+    rr.ffi.check(lib.rr_device_memset(0, p, 0, 256))
+    a, b = torch.cuda.Stream(), torch.cuda.Stream()
+    # b waits for word 3 to reach 7; a publishes 5 (not enough), then 9
+    rr.ffi.check(lib.rr_fence_wait_device(0, C.c_void_p(p.value + 12), 1, 7, 20000, C.c_void_p(p.value + 64), C.c_void_p(b.cuda_stream)))
+    rr.ffi.check(lib.rr_fence_signal_device(0, C.c_void_p(p.value + 16), 1, C.c_void_p(b.cuda_stream)))   # ordered behind the wait
+    rr.ffi.check(lib.rr_fence_signal_device(0, C.c_void_p(p.value + 12), 5, C.c_void_p(a.cuda_stream)))
+    a.synchronize()
+    words = (C.c_uint32 * 64)()
+    rr.ffi.check(lib.rr_device_read(0, p, words, 256))
+    assert words[3] == 5 and words[4] == 0          # the waiter is still spinning: its follow-up store has not happened
+    rr.ffi.check(lib.rr_fence_signal_device(0, C.c_void_p(p.value + 12), 9, C.c_void_p(a.cuda_stream)))
+    torch.cuda.synchronize()
+    rr.ffi.check(lib.rr_device_read(0, p, words, 256))
+    assert words[3] == 9 and words[4] == 1 and words[16] == 0   # released, no timeout recorded
+    assert lib.rr_fence_signal_device(0, None, 1, None) == rr.ffi.RR_ERR_BAD_ARG
+    rr.ffi.check(lib.rr_device_free(0, p))

@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--band-rows", type=int, default=None, help="rows per interleaved band of the multi-GPU shard (default 16)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps or 10
@@ -229,9 +230,10 @@ def main():
     ren = make_env(rr, name)
     scene = rr.DeviceScene(ren, local_rank)
     sharded = world > 1
-    p = ren.frame_params(BAND_ROWS, rank, world) if sharded else ren.frame_params()
+    band_rows = args.band_rows or BAND_ROWS
+    p = ren.frame_params(band_rows, rank, world) if sharded else ren.frame_params()
     my_rows = rr.frame_rows(p)
-    max_rows = bands.max_shard_rows(H, BAND_ROWS, world) if sharded else H
+    max_rows = bands.max_shard_rows(H, band_rows, world) if sharded else H
     shard_bytes = max_rows * W * 3
     frame_bytes = H * W * 3
 
@@ -550,7 +552,7 @@ def main():
         "config": {"workload": name, "width": W, "height": H, "mode": "raymarch" if march else "raytrace",
                    "max_reflections": 3, "max_refractions": 10, "rays_per_frame": rays, "ray_classes": counts,
                    "l2": "flushed between timed steps (256 MiB write, untimed)",
-                   "parallelism": f"row-bands{world}x{BAND_ROWS}, kernel stores rows AND its completion word into rank 0's memory over NVLink (CUDA IPC), rank 0 waits on the words; no collective"
+                   "parallelism": f"row-bands{world}x{band_rows}, kernel stores rows AND its completion word into rank 0's memory over NVLink (CUDA IPC), rank 0 waits on the words; no collective"
                    if sharded else "1gpu",
                    "scene_resident": True},
         "frame_ms": ms_per_step,

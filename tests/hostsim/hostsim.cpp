@@ -6,6 +6,7 @@
 #include "../../include/rr_ffi.h"
 #include "../../ray-rust_b200/csrc/rr_trace.cuh"
 #include "../../ray-rust_b200/csrc/rr_march.cuh"
+#include "../../ray-rust_b200/csrc/rr_bvh.h"
 
 #include <vector>
 
@@ -19,6 +20,9 @@ struct Flat {
     std::vector<int4> obj_b;
     std::vector<DevMaterial> mats;
     std::vector<DevTexture> tex;
+    Bvh bvh;                                  // same builder as the library (csrc/rr_bvh.h)
+    std::vector<float4> bsph;
+    std::vector<int> bsph_oi;
     DevScene G{};
     SceneHead H{};
 };
@@ -58,6 +62,14 @@ void flatten(const rr_scene_desc *d, Flat &f) {
     G.sph = f.sph.data(); G.sph_oi = f.sph_oi.data(); G.sph_m = f.sph_m.data(); G.sph_glow = f.sph_glow.data();
     G.flo_o = f.flo_o.data(); G.flo_n = f.flo_n.data(); G.flo_oi = f.flo_oi.data();
     G.obj_a = f.obj_a.data(); G.obj_n = f.obj_n.data(); G.obj_b = f.obj_b.data(); G.mat = f.mats.data(); G.tex = f.tex.data();
+    if (build_bvh(f.sph_m, f.bvh)) {          // mirrors rr_scene_create (rr_ffi.cu)
+        for (int k : f.bvh.order) { f.bsph.push_back(f.sph[k]); f.bsph_oi.push_back(f.sph_oi[k]); }
+        G.bvh_a = f.bvh.a.data(); G.bvh_b = f.bvh.b.data(); G.bvh_w = f.bvh.w.data();
+        G.bsph = f.bsph.data(); G.bsph_oi = f.bsph_oi.data();
+        G.n_bvh_nodes = (int)f.bvh.a.size(); G.n_bvh_inner = (int)(f.bvh.w.size() / 4);
+        for (int c = 0; c < 3; ++c) { G.scene_lo[c] = f.bvh.lo[c]; G.scene_hi[c] = f.bvh.hi[c]; }
+        G.r_min = f.bvh.r_min;
+    }
     SceneHead &H = f.H;
     for (int k = 0; k < RR_HEAD_SPHERES && k < (int)f.sph.size(); ++k) { H.sph[k] = f.sph[k]; H.sph_oi[k] = f.sph_oi[k]; H.sph_m[k] = f.sph_m[k]; H.sph_glow[k] = f.sph_glow[k]; }
     for (int k = 0; k < RR_HEAD_FLOORS && k < (int)f.flo_o.size(); ++k) { H.flo_o[k] = f.flo_o[k]; H.flo_n[k] = f.flo_n[k]; H.flo_oi[k] = f.flo_oi[k]; }
@@ -88,14 +100,20 @@ FrameParams to_dev(const rr_frame_params *p) {
 }
 }  // namespace
 
-extern "C" int hostsim_render_f32(const rr_scene_desc *desc, const rr_frame_params *params, float *out, rr_ray_counts *counts) {
+// culling: 0 = brute-force scan, 1 = the BVH instance when the builder produces a tree (what the device does by default)
+extern "C" int hostsim_render_f32_ex(const rr_scene_desc *desc, const rr_frame_params *params, float *out, rr_ray_counts *counts,
+                                     int culling, int *used_bvh) {
     Flat f;
     flatten(desc, f);
     FrameParams P = to_dev(params);
     Counters cnt{};
     SceneView S{};
     S.sph = f.G.sph; S.sph_oi = f.G.sph_oi; S.flo_o = f.G.flo_o; S.flo_n = f.G.flo_n; S.flo_oi = f.G.flo_oi;
-    S.n_spheres = f.G.n_spheres; S.n_floors = f.G.n_floors; S.n_bvh_nodes = 0;
+    S.n_spheres = f.G.n_spheres; S.n_floors = f.G.n_floors;
+    const bool bvh = culling && f.G.n_bvh_nodes > 0;
+    S.bvh_a = f.G.bvh_a; S.bvh_b = f.G.bvh_b; S.bvh_w = f.G.bvh_w; S.bsph = f.G.bsph; S.bsph_oi = f.G.bsph_oi;
+    S.n_bvh_nodes = bvh ? f.G.n_bvh_nodes : 0;
+    if (used_bvh) *used_bvh = bvh ? 1 : 0;
     MarchView M{};
     M.sph = f.G.sph_m; M.sph_glow = f.G.sph_glow; M.sph_oi = f.G.sph_oi; M.flo_o = f.G.flo_o; M.flo_n = f.G.flo_n; M.flo_oi = f.G.flo_oi;
     M.n_spheres = f.G.n_spheres; M.n_floors = f.G.n_floors;
@@ -103,7 +121,7 @@ extern "C" int hostsim_render_f32(const rr_scene_desc *desc, const rr_frame_para
     for (int iy = 0; iy < P.yres; ++iy)
         for (int ix = 0; ix < P.xres; ++ix) {
             V3 c;
-            if (!P.use_raymarching) c = trace_pixel<true, false>(f.G, f.H, S, P, ix, iy, cnt);
+            if (!P.use_raymarching) c = bvh ? trace_pixel<true, true>(f.G, f.H, S, P, ix, iy, cnt) : trace_pixel<true, false>(f.G, f.H, S, P, ix, iy, cnt);
             else if (glow == 0) c = march_pixel<true, 0>(f.G, f.H, M, P, ix, iy, cnt);
             else if (glow == 1) c = march_pixel<true, 1>(f.G, f.H, M, P, ix, iy, cnt);
             else c = march_pixel<true, 2>(f.G, f.H, M, P, ix, iy, cnt);
@@ -116,4 +134,8 @@ extern "C" int hostsim_render_f32(const rr_scene_desc *desc, const rr_frame_para
         counts->bg_evals = cnt.bg_evals; counts->sphere_tests = cnt.sphere_tests; counts->sphere_hits = cnt.sphere_hits;
     }
     return 0;
+}
+
+extern "C" int hostsim_render_f32(const rr_scene_desc *desc, const rr_frame_params *params, float *out, rr_ray_counts *counts) {
+    return hostsim_render_f32_ex(desc, params, out, counts, 0, nullptr);
 }

@@ -1,7 +1,8 @@
 """CPU check of the KERNEL SOURCE LOGIC: ray-rust_b200/csrc/rr_trace.cuh and rr_march.cuh are compiled for the
 host (tests/hostsim, CUDA built-ins replaced by stand-ins, -ffp-contract=off) and every pixel is compared with the
 oracle. This runs in the no-GPU container, so a logic regression in trace_pixel/march_pixel is caught before a
-GPU is involved. (GPU code generation, the BVH instance and the store path are covered by the -m gpu tests.)"""
+GPU is involved, including the exact BVH cull (host builder csrc/rr_bvh.h + bvh_scan_ordered). (GPU code generation and
+the store path are covered by the -m gpu tests.)"""
 import ctypes as C
 import os
 import subprocess
@@ -19,7 +20,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def hostsim(rr):
     so = os.path.join(HS, "libhostsim.so")
     deps = [os.path.join(HS, f) for f in ("hostsim.cpp", "cuda_stub.h")] + [
-        os.path.join(ROOT, "ray-rust_b200", "csrc", f) for f in ("rr_device.cuh", "rr_trace.cuh", "rr_march.cuh")]
+        os.path.join(ROOT, "ray-rust_b200", "csrc", f) for f in ("rr_device.cuh", "rr_trace.cuh", "rr_march.cuh", "rr_bvh.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
                                "-o", so, os.path.join(HS, "hostsim.cpp")])
@@ -27,20 +28,26 @@ def hostsim(rr):
     lib.hostsim_render_f32.argtypes = [C.POINTER(rr.ffi.rr_scene_desc), C.POINTER(rr.ffi.rr_frame_params), C.c_void_p,
                                        C.POINTER(rr.ffi.rr_ray_counts)]
 
-    def render(ren):
+    lib.hostsim_render_f32_ex.argtypes = lib.hostsim_render_f32.argtypes + [C.c_int, C.POINTER(C.c_int)]
+
+    def render(ren, culling=False):
         flat = ren.flatten()
         p = ren.frame_params()
         out = np.empty((p.yres, p.xres, 3), dtype=np.float32)
         cnt = rr.ffi.rr_ray_counts()
-        assert lib.hostsim_render_f32(C.byref(flat.desc), C.byref(p), out.ctypes.data_as(C.c_void_p), C.byref(cnt)) == 0
+        used = C.c_int(0)
+        assert lib.hostsim_render_f32_ex(C.byref(flat.desc), C.byref(p), out.ctypes.data_as(C.c_void_p), C.byref(cnt),
+                                         1 if culling else 0, C.byref(used)) == 0
+        if culling:
+            assert used.value == 1, "the builder produced no tree for this scene"
         return out, cnt
 
     return render
 
 
-def _check(ren, oracle, hostsim):
-    ref = oracle.render(ren, want_f32=True, want_tags=True, want_counts=True)
-    out, cnt = hostsim(ren)
+def _check(ren, oracle, hostsim, culling=False):
+    ref = oracle.render(ren, threads=os.cpu_count() or 1, want_f32=True, want_tags=True, want_counts=True)
+    out, cnt = hostsim(ren, culling)
     # same libm on both sides here, so even bgcolor / glow pixels must agree bit for bit
     a, b = out.view(np.uint32), ref["f32"].view(np.uint32)
     nan = np.isnan(out)
@@ -64,3 +71,39 @@ def test_random_scenes_logic(rr, oracle, hostsim, march):
 
     for seed in range(12 if not march else 5):
         _check(_random_env(rr, 1000 + seed + (500 if march else 0), march), oracle, hostsim)
+
+
+def test_bvh_logic_synthetic(rr, oracle, hostsim):
+    """The BVH instance (SAH build, ordered stack traversal, FMA slabs) against the brute-force oracle, bit for bit."""
+    _check(rr.synthetic_scene(96, 54, n_spheres=300), oracle, hostsim, culling=True)
+    _check(rr.synthetic_scene(64, 36, n_spheres=1024), oracle, hostsim, culling=True)
+    _check(rr.synthetic_scene(48, 27, n_spheres=24, seed=7), oracle, hostsim, culling=True)   # smallest tree
+
+
+def test_bvh_logic_hard_cases(rr, oracle, hostsim):
+    """Duplicates (exact ties: lowest index must win whatever the visiting order), tiny and huge spheres, a camera
+    inside a sphere, and a scene far from the coordinate origin (the FMA slab form rounds (o +- e)/d on its own)."""
+    from ray_rust_b200.scene import RenderColor, RenderMaterial, RenderSphere, RenderFloor
+
+    def env(spheres, cam=(0.0, -150.0, -300.0), floor_y=300.0):
+        mats = {
+            "m": RenderMaterial.new("m", RenderColor(0.8, 0.2, 0.2), RenderColor(0.3, 0.3, 0.3), 24, 0.0, 0.0),
+            "g": RenderMaterial.new("g", RenderColor(0.0, 0.0, 0.0), RenderColor(0.2, 0.2, 0.2), 0, 0.8, 1.5),
+            "f": RenderMaterial.new("f", RenderColor(1.0, 1.0, 0.0), RenderColor(0.0, 0.0, 0.0), 0, 0.0, 0.0).pattern("Checkerboard").pattern_scale(100.0),
+        }
+        objs = [RenderFloor.new(mats["f"], (cam[0], floor_y, cam[2]), (0.0, -1.0, 0.0))]
+        for i, (c, r) in enumerate(spheres):
+            objs.append(RenderSphere.new(mats["g" if i % 3 == 0 else "m"], r, c))
+        base = rr.default_scene(72, 40)
+        ren = rr.RenderEnv.new(cam, tuple(base.camera.pyr), 72, 40, 1.0, 40.0 / 72.0)
+        return ren.materials(mats).objects(objs).light((50.0, 60.0, -50.0))
+
+    rng = np.random.default_rng(5)
+    pts = [((float(x), float(y), float(z)), float(r)) for x, y, z, r in
+           zip(rng.uniform(-400, 400, 40), rng.uniform(-200, 200, 40), rng.uniform(0, 900, 40), rng.uniform(5, 60, 40))]
+    _check(env(pts + pts[:10]), oracle, hostsim, culling=True)                                       # exact duplicates
+    _check(env(pts + [((0.0, 0.0, 400.0), 1e-3), ((50.0, 0.0, 500.0), 700.0)]), oracle, hostsim, culling=True)
+    _check(env(pts + [((0.0, -150.0, -300.0), 90.0)]), oracle, hostsim, culling=True)                # camera inside a glass sphere
+    off = (1.0e6, -2.0e6, 3.0e6)
+    far = [((c[0] + off[0], c[1] + off[1], c[2] + off[2]), r) for c, r in pts]
+    _check(env(far, cam=(off[0], off[1] - 150.0, off[2] - 300.0), floor_y=off[1] + 300.0), oracle, hostsim, culling=True)

@@ -377,7 +377,7 @@ int rr_scene_create(const rr_scene_desc *desc, int device, rr_scene **out) {
         return bail(fail_cuda(e, "rr_scene_create"));
     s->allocs.push_back(s->d_cnt);
     s->allocs.push_back(s->d_work);
-    if ((e = cudaMemset(s->d_work, 0, 64)) != cudaSuccess) return bail(fail_cuda(e, "cudaMemset"));
+    if ((e = cudaMemset(s->d_work, 0, 512)) != cudaSuccess) return bail(fail_cuda(e, "cudaMemset"));
     if ((e = rr::preload_signal_kernels()) != cudaSuccess) return bail(fail_cuda(e, "preload"));
     for (auto &ev : s->chunk_ev)
         if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));

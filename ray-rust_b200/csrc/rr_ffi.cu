@@ -127,7 +127,7 @@ int launch(rr_scene *s, const rr::FrameParams &P, void *d_out, size_t row_stride
     unsigned *slot = s->d_work + 16 + 4 * (s->launch_seq++ & 15u);
     const rr::Signal sig{slot, slot + 1, d_flag, epoch};
     const bool fused = d_flag && !P.use_raymarching && P.xres > 0 && P.local_rows > 0;
-    cudaError_t e = P.use_raymarching ? rr::launch_march(s->G, s->H, P, d_out, row_stride, f32, d_cnt, s->d_work, st, s->li)
+    cudaError_t e = P.use_raymarching ? rr::launch_march(s->G, s->H, P, d_out, row_stride, f32, d_cnt, s->d_work, st, s->li, s->culling)
                                       : rr::launch_trace(s->G, s->H, P, d_out, row_stride, f32, d_cnt, st, s->li, s->culling, sig);
     if (e == cudaSuccess && d_flag && !fused) e = rr::launch_signal(sig, st);
     if (e != cudaSuccess) return fail_cuda(e, "kernel launch");

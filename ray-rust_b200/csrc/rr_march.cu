@@ -22,6 +22,10 @@ __device__ __forceinline__ MarchView stage_march(const DevScene &G, float4 *smem
     S.n_spheres = G.n_spheres;
     S.n_floors = G.n_floors;
     S.sph = G.sph_m; S.sph_glow = G.sph_glow; S.sph_oi = G.sph_oi; S.flo_o = G.flo_o; S.flo_n = G.flo_n; S.flo_oi = G.flo_oi;
+    // MBVH instances read the BVH and the leaf-ordered spheres from global memory through L1 (40 KB for 1 024 spheres)
+    S.bvh_a = G.bvh_a; S.bvh_b = G.bvh_b; S.bsph = G.bsph_m; S.bsph_oi = G.bsph_oi; S.n_bvh_nodes = G.n_bvh_nodes;
+    S.scene_abs = 0.0f;
+    for (int k = 0; k < 3; ++k) S.scene_abs = fmaxf(S.scene_abs, fmaxf(fabsf(G.scene_lo[k]), fabsf(G.scene_hi[k])));
     if (!stage) return S;
     const int ts = max(G.n_spheres - RR_HEAD_SPHERES, 0), tf = max(G.n_floors - RR_HEAD_FLOORS, 0);
     if (ts + tf == 0) return S;
@@ -44,7 +48,7 @@ __device__ __forceinline__ MarchView stage_march(const DevScene &G, float4 *smem
     return S;
 }
 
-template <bool COUNT, bool F32OUT, bool STAGE, int GLOW>
+template <bool COUNT, bool F32OUT, bool STAGE, int GLOW, bool MBVH>
 __global__ void __launch_bounds__(MARCH_THREADS)
 march_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHead H, const __grid_constant__ FrameParams P,
              void *__restrict__ out, size_t row_stride, Counters *gcnt, unsigned *work, int fast_store) {
@@ -68,7 +72,7 @@ march_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
         const int ix = x0 + col, ly = ly0 + row;
         const bool valid = ix < W && ly < rows;
         V3 c = mk(0.0f, 0.0f, 0.0f);
-        if (valid) c = march_pixel<COUNT, GLOW>(G, H, S, P, ix, local_to_image_row(P, ly), cnt);
+        if (valid) c = march_pixel<COUNT, GLOW, MBVH>(G, H, S, P, ix, local_to_image_row(P, ly), cnt);
         if (F32OUT) {
             if (valid) {
                 float *o = reinterpret_cast<float *>(out) + ((size_t)(P.placed ? local_to_image_row(P, ly) : ly) * W + ix) * 3;
@@ -89,10 +93,10 @@ static size_t march_smem_bytes(const DevScene &G) {
     return ts * (sizeof(float4) + sizeof(float) + sizeof(int)) + tf * (2 * sizeof(float4) + sizeof(int)) + 16;
 }
 
-template <bool COUNT, bool F32OUT, bool STAGE, int GLOW>
+template <bool COUNT, bool F32OUT, bool STAGE, int GLOW, bool MBVH = false>
 static cudaError_t launch_one(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
                               Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li, size_t smem) {
-    auto kern = march_kernel<COUNT, F32OUT, STAGE, GLOW>;
+    auto kern = march_kernel<COUNT, F32OUT, STAGE, GLOW, MBVH>;
     cudaError_t e;
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -116,13 +120,19 @@ static cudaError_t launch_one(const DevScene &G, const SceneHead &H, const Frame
 
 template <bool COUNT, bool F32OUT>
 static cudaError_t launch_two(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
-                              Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li) {
+                              Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh) {
     size_t smem = march_smem_bytes(G);
     const bool stage = smem <= li.smem_optin / 2;
     if (!stage) smem = 0;
     // glow tracking: 0 = nothing reads it, 1 = separate pass over the <= RR_HEAD_GLOW glowing objects,
     // 2 = inline in the scan (many glowing objects)
     const int glow = !(P.glow_enabled && G.n_glow > 0) ? 0 : (H.n_glow_head >= 0 ? 1 : 2);
+    // Large scenes: the sphere scan goes through the BVH (rr_march.cuh, MBVH); nothing is staged (floor tails and BVH are
+    // read through L1). Inline glow keeps the linear scan.
+    if (allow_bvh && G.n_bvh_nodes > 0 && glow != 2) {
+        if (glow == 0) return launch_one<COUNT, F32OUT, false, 0, true>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, 0);
+        return launch_one<COUNT, F32OUT, false, 1, true>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, 0);
+    }
     if (stage) {
         if (glow == 0) return launch_one<COUNT, F32OUT, true, 0>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, smem);
         if (glow == 1) return launch_one<COUNT, F32OUT, true, 1>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, smem);
@@ -134,12 +144,12 @@ static cudaError_t launch_two(const DevScene &G, const SceneHead &H, const Frame
 }
 
 cudaError_t launch_march(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
-                         bool f32_out, Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li) {
+                         bool f32_out, Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh) {
     if (P.xres <= 0 || P.local_rows <= 0) return cudaSuccess;
-    if (d_cnt) return f32_out ? launch_two<true, true>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li)
-                              : launch_two<true, false>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li);
-    return f32_out ? launch_two<false, true>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li)
-                   : launch_two<false, false>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li);
+    if (d_cnt) return f32_out ? launch_two<true, true>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, allow_bvh)
+                              : launch_two<true, false>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, allow_bvh);
+    return f32_out ? launch_two<false, true>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, allow_bvh)
+                   : launch_two<false, false>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, allow_bvh);
 }
 
 }  // namespace rr

@@ -31,6 +31,11 @@ struct MarchView {  // list tails (shared memory when staged), indexed with the 
     const float4 *flo_n;
     const int *flo_oi;
     int n_spheres, n_floors;
+    // large scenes (MBVH instances): the trace kernel's depth-first BVH arrays and the leaf-ordered (cx, cy, cz, r) copy
+    const float4 *bvh_a, *bvh_b, *bsph;
+    const int *bsph_oi;
+    int n_bvh_nodes;
+    float scene_abs;  // largest |coordinate| of the scene bounds
 };
 
 struct MarchResult {  // render.rs:1257-1264
@@ -87,6 +92,36 @@ __device__ __forceinline__ void sphere_dist(const float4 &c, float glow, int oi,
     }
 }
 
+// glow pass (render.rs:1244-1247) over the few glowing objects only (GLOW == 1); see distance_estimate
+__device__ __forceinline__ void glow_pass(const SceneHead &H, const V3 &vi, int ig, float &gl) {
+    // glow pass (render.rs:1244-1247) over the few glowing objects only; their distance is formed
+    // with the same operations as in the scan, so the bits are the same whether or not the scan
+    // above skipped the object's sqrt.
+    // Sqrt skip: a glowing sphere (r >= 0, k = glow_dist > 0; the host stores glow_ik = fl(1/k), NaN otherwise) can
+    // only lower gl if fl(dist * k) < gl. With T = fl(fl(gl * ik) + r) >= (gl/k + r)(1 - 3u): sq > fl(fl(T*T) * 1.00002)
+    // implies sqrt(sq) >= (gl/k + r)(1 + 9.3e-6), dist >= (gl/k)(1 + 9.2e-6), fl(dist * k) > gl: no update. gl = inf or a
+    // NaN anywhere makes the comparison false and the value is computed.
+#pragma unroll 1
+    for (int g = 0; g < H.n_glow_head; ++g) {  // rolled: keeps the march loop inside the L0 I-cache
+        if (H.glow_oi[g] != ig) {
+            const float4 a = H.glow_a[g];
+            float dist;
+            if (H.glow_kind[g] == 0) {
+                const V3 d = mk(a.x, a.y, a.z) - vi;
+                const float sq = d.x * d.x + d.y * d.y + d.z * d.z;
+                const float T = gl * H.glow_ik[g] + a.w;
+                if (sq > T * T * 1.00002f) continue;
+                dist = fmaxf(sqrtf(sq) - a.w, 0.0f);
+            } else {
+                const float4 nn = H.glow_b[g];
+                dist = fmaxf(dot(vi - mk(a.x, a.y, a.z), mk(nn.x, nn.y, nn.z)), 0.0f);
+            }
+            const float gv = dist * H.glow_k[g];
+            if (0.0f < gv && gv < gl) gl = gv;
+        }
+    }
+}
+
 // distance_estimate, render.rs:1226-1251. `glowing` is in/out: the smallest glow value seen so far by the caller
 // (render.rs:1281 takes the minimum over the march, :1331 over the marches of a frame; only that minimum is used).
 //
@@ -96,7 +131,17 @@ __device__ __forceinline__ void sphere_dist(const float4 &c, float glow, int oi,
 // |C - p| =: x > (best + R)(1 + 4.4e-6), and the distance the reference computes for s, fl(fl(sqrt(sq_s)) - r_s), is
 // >= (x - R) - 3.5u (x + R) - u x >= best (1 + 4.1e-6) + 3.9e-6 R > best: no head sphere can lower or tie the running
 // minimum, exactly the situation in which sphere_dist() returns early for each of them. best = inf or NaN never skips.
-template <int GLOW>
+//
+// Large scenes (MBVH): the spheres are visited through the BVH the trace kernel uses (stackless depth-first order with
+// escape indices; leaves hold <= 4 spheres), pruned by point-to-box distance. A node box holds the balls of its spheres
+// up to the f32 rounding of its corners (<= u S, S = scene_abs). With m = 3e-6 (|p|_inf + S): d2 > fl(fl(T*T) * 1.00001),
+// T = fl(best + m), d2 the f32 squared distance from p to the box, implies dist(p, box) > (best + m)(1 + 4.5e-6), hence for
+// every sphere below the node |c_s - p| - r_s > best + m - 1.1e-7 S, and the distance the reference computes for it,
+// fl(fl(sqrt(sq_s)) - r_s) >= that - 3.5u |c_s - p| - u rho_s >= best + m - 7e-7 (|p|_inf + S) > best: it can neither lower
+// nor tie the running minimum. Leaves run the unchanged sphere_dist() (with its own exact sqrt skip), so the visiting
+// order does not matter either (ties go to the lowest original index there). Inline glow (GLOW == 2) is not combined
+// with this instance: the launcher keeps the linear scan for it.
+template <int GLOW, bool MBVH = false>
 __device__ __forceinline__ void distance_estimate(const SceneHead &H, const MarchView &S, const V3 &vi, int ig, bool track,
                                                   float &closest, int &idx_out, float &glowing, bool &all_far) {
     float best = RR_INF, gl = glowing;
@@ -106,6 +151,36 @@ __device__ __forceinline__ void distance_estimate(const SceneHead &H, const Marc
         if (f < S.n_floors) floor_dist<GLOW>(H.flo_o[f], H.flo_n[f], H.flo_oi[f], vi, ig, track, best, idx, gl);
     for (int f = RR_HEAD_FLOORS; f < S.n_floors; ++f)
         floor_dist<GLOW>(S.flo_o[f], S.flo_n[f], S.flo_oi[f], vi, ig, track, best, idx, gl);
+    if constexpr (MBVH) {
+        static_assert(GLOW != 2, "inline glow needs every glowing object's distance: linear scan only");
+        const float m = 3e-6f * (fmaxf(fmaxf(fabsf(vi.x), fabsf(vi.y)), fabsf(vi.z)) + S.scene_abs);
+        int node = 0;
+        while (node < S.n_bvh_nodes) {
+            const float4 a = S.bvh_a[node], b = S.bvh_b[node];
+            const float dx = fmaxf(fmaxf(a.x - vi.x, vi.x - b.x), 0.0f);
+            const float dy = fmaxf(fmaxf(a.y - vi.y, vi.y - b.y), 0.0f);
+            const float dz = fmaxf(fmaxf(a.z - vi.z, vi.z - b.z), 0.0f);
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            const float T = best + m;
+            const int leaf = __float_as_int(b.w);
+            if (d2 > T * T * 1.00001f) {  // best = inf or a NaN anywhere: false, the subtree is visited
+                node = __float_as_int(a.w);
+            } else if (leaf < 0) {
+                node = node + 1;
+            } else {
+                const int first = leaf >> 3, count = leaf & 7;
+                for (int k = 0; k < count; ++k)
+                    sphere_dist<GLOW>(S.bsph[first + k], 0.0f, S.bsph_oi[first + k], vi, ig, track, best, idx, gl);
+                node = __float_as_int(a.w);
+            }
+        }
+        if (GLOW == 1 && track) glow_pass(H, vi, ig, gl);
+        closest = best;
+        idx_out = idx;
+        glowing = gl;
+        all_far = false;
+        return;
+    }
     // The same sphere also bounds the glowing spheres of the glow pass when the host says so (H.grp_ik = fl(1 / k_min),
     // k_min the smallest glow_dist, NaN otherwise): with x = |C - p| > (gl / k_min + R)(1 + 9.3e-6) every glowing sphere g
     // has fl(dist_g * k_g) >= (x - R - 3.5u (x + R) - u x) k_min (1 - u) > gl, so the whole pass cannot lower gl.
@@ -128,34 +203,7 @@ __device__ __forceinline__ void distance_estimate(const SceneHead &H, const Marc
 #pragma unroll 2
     for (int s = RR_HEAD_SPHERES; s < S.n_spheres; ++s)
         sphere_dist<GLOW>(S.sph[s], GLOW == 2 ? S.sph_glow[s] : 0.0f, S.sph_oi[s], vi, ig, track, best, idx, gl);
-    if (GLOW == 1 && track && !glow_far) {
-        // glow pass (render.rs:1244-1247) over the few glowing objects only; their distance is formed
-        // with the same operations as in the scan, so the bits are the same whether or not the scan
-        // above skipped the object's sqrt.
-        // Sqrt skip: a glowing sphere (r >= 0, k = glow_dist > 0; the host stores glow_ik = fl(1/k), NaN otherwise) can
-        // only lower gl if fl(dist * k) < gl. With T = fl(fl(gl * ik) + r) >= (gl/k + r)(1 - 3u): sq > fl(fl(T*T) * 1.00002)
-        // implies sqrt(sq) >= (gl/k + r)(1 + 9.3e-6), dist >= (gl/k)(1 + 9.2e-6), fl(dist * k) > gl: no update. gl = inf or a
-        // NaN anywhere makes the comparison false and the value is computed.
-#pragma unroll 1
-        for (int g = 0; g < H.n_glow_head; ++g) {  // rolled: keeps the march loop inside the L0 I-cache
-            if (H.glow_oi[g] != ig) {
-                const float4 a = H.glow_a[g];
-                float dist;
-                if (H.glow_kind[g] == 0) {
-                    const V3 d = mk(a.x, a.y, a.z) - vi;
-                    const float sq = d.x * d.x + d.y * d.y + d.z * d.z;
-                    const float T = gl * H.glow_ik[g] + a.w;
-                    if (sq > T * T * 1.00002f) continue;
-                    dist = fmaxf(sqrtf(sq) - a.w, 0.0f);
-                } else {
-                    const float4 nn = H.glow_b[g];
-                    dist = fmaxf(dot(vi - mk(a.x, a.y, a.z), mk(nn.x, nn.y, nn.z)), 0.0f);
-                }
-                const float gv = dist * H.glow_k[g];
-                if (0.0f < gv && gv < gl) gl = gv;
-            }
-        }
-    }
+    if (GLOW == 1 && track && !glow_far) glow_pass(H, vi, ig, gl);
     closest = best;
     idx_out = idx;
     glowing = gl;
@@ -189,14 +237,14 @@ __device__ __forceinline__ bool spheres_far(const SceneHead &H, const V3 &vi, bo
 // arithmetic distance_estimate() + the step update would perform for such a step (same operations, same order, idx = the
 // floor's index); anything else (a NaN or infinite distance, a failed test, an ignored floor, more floors or
 // spheres than the head holds, inline glow) leaves it without having changed any state and takes the full step.
-template <int GLOW>
+template <int GLOW, bool MBVH = false>
 __device__ __forceinline__ MarchResult raymarch_single(const SceneHead &H, const MarchView &S, const V3 &init_pos,
                                                        const V3 &eye, int ig, bool track, float glow_bound) {
     int iter = 0;
     float travel = 0.0f;
     V3 pos = init_pos;
     float min_dist = glow_bound;
-    const bool creep_ok = RR_HEAD_FLOORS >= 1 && S.n_floors == 1 && S.n_spheres <= RR_HEAD_SPHERES && H.flo_oi[0] != ig &&
+    const bool creep_ok = !MBVH && RR_HEAD_FLOORS >= 1 && S.n_floors == 1 && S.n_spheres <= RR_HEAD_SPHERES && H.flo_oi[0] != ig &&
                           H.grp.w >= 0.0f && !(GLOW == 2 && track);
     // ONE loop: in every iteration a lane takes either the creeping step or the full step, so that the lanes of a warp
     // advance together (an inner creeping loop would make the lanes that need full steps wait for thousands of
@@ -220,7 +268,7 @@ __device__ __forceinline__ MarchResult raymarch_single(const SceneHead &H, const
         float dist;
         int idx;
         bool all_far;
-        distance_estimate<GLOW>(H, S, pos, ig, track, dist, idx, min_dist, all_far);
+        distance_estimate<GLOW, MBVH>(H, S, pos, ig, track, dist, idx, min_dist, all_far);
         pos = (eye * dist) + pos;
         travel += dist;
         iter += 1;
@@ -252,7 +300,7 @@ __device__ __forceinline__ V3 apply_glow(const FrameParams &P, const V3 &c, floa
     return mk(factor * c.x, factor * c.y, factor * c.z);
 }
 
-template <bool COUNT, int GLOW>
+template <bool COUNT, int GLOW, bool MBVH = false>
 __device__ __forceinline__ V3 march_pixel(const DevScene &G, const SceneHead &H, const MarchView &S, const FrameParams &P,
                                           int ix, int iy, Counters &cnt) {
     const V3 light = mk(P.light[0], P.light[1], P.light[2]);
@@ -280,7 +328,7 @@ __device__ __forceinline__ V3 march_pixel(const DevScene &G, const SceneHead &H,
             ro = pt + (light * F32_EPSILON);  // render.rs:1034
             rd = light; rig = hidx;
         }
-        const MarchResult r = raymarch_single<GLOW>(H, S, ro, rd, rig, !shadow_phase, shadow_phase ? RR_INF : mmd);
+        const MarchResult r = raymarch_single<GLOW, MBVH>(H, S, ro, rd, rig, !shadow_phase, shadow_phase ? RR_INF : mmd);
         if (COUNT) {
             if (shadow_phase) {
                 cnt.shadow++;

@@ -21,7 +21,7 @@ struct Flat {
     std::vector<DevMaterial> mats;
     std::vector<DevTexture> tex;
     Bvh bvh;                                  // same builder as the library (csrc/rr_bvh.h)
-    std::vector<float4> bsph;
+    std::vector<float4> bsph, bsph_m;
     std::vector<int> bsph_oi;
     DevScene G{};
     SceneHead H{};
@@ -63,9 +63,9 @@ void flatten(const rr_scene_desc *d, Flat &f) {
     G.flo_o = f.flo_o.data(); G.flo_n = f.flo_n.data(); G.flo_oi = f.flo_oi.data();
     G.obj_a = f.obj_a.data(); G.obj_n = f.obj_n.data(); G.obj_b = f.obj_b.data(); G.mat = f.mats.data(); G.tex = f.tex.data();
     if (build_bvh(f.sph_m, f.bvh)) {          // mirrors rr_scene_create (rr_ffi.cu)
-        for (int k : f.bvh.order) { f.bsph.push_back(f.sph[k]); f.bsph_oi.push_back(f.sph_oi[k]); }
+        for (int k : f.bvh.order) { f.bsph.push_back(f.sph[k]); f.bsph_m.push_back(f.sph_m[k]); f.bsph_oi.push_back(f.sph_oi[k]); }
         G.bvh_a = f.bvh.a.data(); G.bvh_b = f.bvh.b.data(); G.bvh_w = f.bvh.w.data();
-        G.bsph = f.bsph.data(); G.bsph_oi = f.bsph_oi.data();
+        G.bsph = f.bsph.data(); G.bsph_m = f.bsph_m.data(); G.bsph_oi = f.bsph_oi.data();
         G.n_bvh_nodes = (int)f.bvh.a.size(); G.n_bvh_inner = (int)(f.bvh.w.size() / 4);
         for (int c = 0; c < 3; ++c) { G.scene_lo[c] = f.bvh.lo[c]; G.scene_hi[c] = f.bvh.hi[c]; }
         G.r_min = f.bvh.r_min;
@@ -118,10 +118,17 @@ extern "C" int hostsim_render_f32_ex(const rr_scene_desc *desc, const rr_frame_p
     M.sph = f.G.sph_m; M.sph_glow = f.G.sph_glow; M.sph_oi = f.G.sph_oi; M.flo_o = f.G.flo_o; M.flo_n = f.G.flo_n; M.flo_oi = f.G.flo_oi;
     M.n_spheres = f.G.n_spheres; M.n_floors = f.G.n_floors;
     const int glow = !(P.glow_enabled && f.G.n_glow > 0) ? 0 : (f.H.n_glow_head >= 0 ? 1 : 2);
+    const bool mbvh = P.use_raymarching && culling && f.G.n_bvh_nodes > 0 && glow != 2;  // as launch_two (rr_march.cu)
+    M.bvh_a = f.G.bvh_a; M.bvh_b = f.G.bvh_b; M.bsph = f.G.bsph_m; M.bsph_oi = f.G.bsph_oi; M.n_bvh_nodes = f.G.n_bvh_nodes;
+    M.scene_abs = 0.0f;
+    for (int k = 0; k < 3; ++k) M.scene_abs = fmaxf(M.scene_abs, fmaxf(fabsf(f.G.scene_lo[k]), fabsf(f.G.scene_hi[k])));
+    if (used_bvh && P.use_raymarching) *used_bvh = mbvh ? 1 : 0;
     for (int iy = 0; iy < P.yres; ++iy)
         for (int ix = 0; ix < P.xres; ++ix) {
             V3 c;
             if (!P.use_raymarching) c = bvh ? trace_pixel<true, true>(f.G, f.H, S, P, ix, iy, cnt) : trace_pixel<true, false>(f.G, f.H, S, P, ix, iy, cnt);
+            else if (mbvh && glow == 0) c = march_pixel<true, 0, true>(f.G, f.H, M, P, ix, iy, cnt);
+            else if (mbvh) c = march_pixel<true, 1, true>(f.G, f.H, M, P, ix, iy, cnt);
             else if (glow == 0) c = march_pixel<true, 0>(f.G, f.H, M, P, ix, iy, cnt);
             else if (glow == 1) c = march_pixel<true, 1>(f.G, f.H, M, P, ix, iy, cnt);
             else c = march_pixel<true, 2>(f.G, f.H, M, P, ix, iy, cnt);

@@ -88,3 +88,27 @@ def test_bvh_far_origins(rr):
     ren.camera.position = (np.float32(0), np.float32(2.0e5), np.float32(-1.0e6))
     a, b, _, _ = _both(rr, ren)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("kw", [dict(seed=21, n=30), dict(seed=22, n=300, dup=True), dict(seed=23, n=150, inside=True),
+                                dict(seed=24, n=700, tiny=True), dict(seed=25, n=100, spread=40.0)])
+@pytest.mark.parametrize("glow", [None, 0.8])
+def test_march_bvh_equals_linear_scan_bits(rr, kw, glow):
+    """Ray-march mode of large scenes: the distance scan pruned through the BVH (MBVH instance) against the linear scan
+    (culling off), f32 bit for bit and byte for byte."""
+    ren = _random_scene(rr, w=96, h=54, **kw)
+    ren.use_raymarching(True).glow_effect(glow)
+    a, b, a8, b8 = _both(rr, ren)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.array_equal(a8, b8)
+
+
+def test_march_bvh_vs_oracle(rr, oracle):
+    ren = rr.synthetic_scene(160, 90, n_spheres=400, use_raymarching=True, glow_effect=1.0)
+    ref = oracle.render(ren, threads=NCPU, want_counts=True)
+    scene = rr.DeviceScene(ren, 0)
+    img, cnt = scene.render_count(ren.frame_params())
+    scene.close()
+    d = np.abs(img.astype(int) - ref["u8"].astype(int)).max(axis=2)
+    assert (d <= 1).mean() >= 0.9995 and (d == 0).mean() >= 0.995, ((d == 0).mean(), d.max())
+    assert cnt.as_dict() == ref["counts"].as_dict()

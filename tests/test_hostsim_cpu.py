@@ -107,3 +107,11 @@ def test_bvh_logic_hard_cases(rr, oracle, hostsim):
     off = (1.0e6, -2.0e6, 3.0e6)
     far = [((c[0] + off[0], c[1] + off[1], c[2] + off[2]), r) for c, r in pts]
     _check(env(far, cam=(off[0], off[1] - 150.0, off[2] - 300.0), floor_y=off[1] + 300.0), oracle, hostsim, culling=True)
+
+
+def test_march_bvh_logic(rr, oracle, hostsim):
+    """Ray-march mode of large scenes: the distance scan pruned through the BVH (point-to-box distance, rr_march.cuh MBVH)
+    against the brute-force oracle, bit for bit, with and without the glow pass, incl. a scene far from the origin."""
+    _check(rr.synthetic_scene(64, 36, n_spheres=300, use_raymarching=True), oracle, hostsim, culling=True)
+    _check(rr.synthetic_scene(48, 27, n_spheres=1024, use_raymarching=True, glow_effect=0.7), oracle, hostsim, culling=True)
+    _check(rr.synthetic_scene(40, 24, n_spheres=24, seed=11, use_raymarching=True, glow_effect=1.0), oracle, hostsim, culling=True)

@@ -24,9 +24,19 @@ def test_reference_arm_json_line():
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
 
 
+def _free_port():
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
 def test_reference_arm_under_torchrun_prints_once():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29731", BENCH, "--impl", "reference", "--gpus", "2", *SMALL]
+           "--master-port", str(_free_port()), BENCH, "--impl", "reference", "--gpus", "2", *SMALL]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]

@@ -76,3 +76,31 @@ def test_nan_camera(rr, oracle):
     ren = _scene(rr, objs, w=16, h=8)
     ren.camera.position = (np.float32("nan"), np.float32(0), np.float32(0))
     _cmp(rr, oracle, ren)
+
+
+@pytest.mark.parametrize("w,h", [(1536, 1003), (2048, 1537), (1283, 997)])
+def test_chunked_host_pipeline_odd_rows(rr, w, h):
+    """rr_render_rgb8's kernel/copy pipeline (geometric chunk plan, chunks of whole 4-row tiles, a ragged last chunk)
+    against one device-resident launch of the same frame, for frames big enough to be chunked, packed and padded."""
+    import ctypes as C
+
+    import torch
+
+    ren = rr.default_scene(w, h)
+    scene = rr.DeviceScene(ren, 0)
+    p = ren.frame_params()
+    dev = torch.empty(h * w * 3, dtype=torch.uint8, device="cuda:0")
+    scene.render_rgb8_device(p, dev.data_ptr())
+    torch.cuda.synchronize()
+    whole = dev.cpu().numpy().reshape(h, w, 3)
+    assert np.array_equal(scene.render_rgb8(p), whole)            # pageable destination
+    stride = w * 3 + 8
+    host = C.c_void_p()
+    rr.ffi.check(scene.lib.rr_host_alloc(stride * h, C.byref(host)))
+    pinned = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_uint8)), shape=(h, stride))
+    pinned[:] = 0xEE
+    rr.ffi.check(scene.lib.rr_render_rgb8(scene.handle, C.byref(p), host, stride))
+    assert np.array_equal(pinned[:, : w * 3].reshape(h, w, 3), whole) and (pinned[:, w * 3:] == 0xEE).all()
+    del pinned
+    scene.lib.rr_host_free(host)
+    scene.close()

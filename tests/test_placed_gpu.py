@@ -158,3 +158,28 @@ def test_fence_signal_memset_read(rr):
     assert words[3] == 9 and words[4] == 1 and words[16] == 0   # released, no timeout recorded
     assert lib.rr_fence_signal_device(0, None, 1, None) == rr.ffi.RR_ERR_BAD_ARG
     rr.ffi.check(lib.rr_device_free(0, p))
+
+
+def test_overlapping_launches_of_one_handle(rr):
+    """Kernels of ONE scene handle queued on several streams run concurrently; each launch owns one of 16 (tile queue,
+    block counter) slots that reset themselves, so 12 overlapping launches on 6 streams must all produce the frame."""
+    import torch
+
+    ren = rr.default_scene(1024, 576)
+    scene = rr.DeviceScene(ren, 0)
+    p = ren.frame_params()
+    ref = torch.empty(576 * 1024 * 3, dtype=torch.uint8, device="cuda:0")
+    scene.render_rgb8_device(p, ref.data_ptr())
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(6)]
+    bufs = [torch.zeros_like(ref) for _ in range(12)]
+    for rep in range(3):                                   # 36 launches in total: the slot ring wraps twice
+        for b in bufs:
+            b.zero_()
+        torch.cuda.synchronize()
+        for i, b in enumerate(bufs):
+            scene.render_rgb8_device(p, b.data_ptr(), stream=streams[i % 6].cuda_stream)
+        torch.cuda.synchronize()
+        for b in bufs:
+            assert torch.equal(b, ref)
+    scene.close()

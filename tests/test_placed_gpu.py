@@ -183,3 +183,21 @@ def test_overlapping_launches_of_one_handle(rr):
         for b in bufs:
             assert torch.equal(b, ref)
     scene.close()
+
+
+def test_shared_device_frame_single_rank(rr):
+    """ray_rust_b200.multi.SharedDeviceFrame with one rank (no process group): render + completion word + wait + download."""
+    from ray_rust_b200.multi import SharedDeviceFrame
+
+    ren = rr.default_scene(640, 360)
+    scene = rr.DeviceScene(ren, 0)
+    frame = SharedDeviceFrame(None, 0, 1, 0, 640, 360)
+    for _ in range(3):
+        frame.render(scene, ren)
+    import torch
+
+    torch.cuda.synchronize()
+    assert frame.epoch == 3 and not frame.timed_out()
+    assert np.array_equal(frame.download(), scene.render_rgb8(ren.frame_params()))
+    frame.close()
+    scene.close()

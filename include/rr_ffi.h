@@ -18,8 +18,9 @@
  *   - All floats are IEEE-754 binary32, all colour channels are linear f32 as in RenderColor
  *     (src/render.rs:23-28); RGB8 output is `(c*255).min(255) as u8` (src/main.rs:148-152).
  *   - A scene handle may be used from several host threads concurrently (the web server calls
- *     render() from several tokio workers, src/webserver.rs:268-280); calls on one handle are
- *     serialised by a per-handle mutex.
+ *     render() from several tokio workers, src/webserver.rs:268-280): up to 4 host-facing renders of
+ *     one handle run concurrently on the device (each on its own stream pair and device frame), a
+ *     fifth waits for a free one; *_device launches on caller streams never wait.
  *   - The device path is the only path: if no CUDA device is usable every entry point fails with
  *     RR_ERR_CUDA. There is no CPU fallback inside this library.
  */
@@ -176,6 +177,16 @@ int rr_frame_rows(const rr_frame_params *params, int32_t *rows_out);
  * Blocking. The timed region of bench.py's `e2e` is exactly one call of this function. */
 int rr_render_rgb8(rr_scene *scene, const rr_frame_params *params, uint8_t *out, size_t row_stride);
 
+/* render_frames() support (src/render.rs:926-989 renders many frames of one scene, one render() + image::save_buffer
+ * per frame). rr_render_rgb8_async enqueues exactly what rr_render_rgb8 does and returns a ticket; rr_render_wait blocks
+ * until that frame is complete in `out` (and reports the device time of its kernels, kernel_ms may be NULL). A handle
+ * keeps up to 4 frames in flight (a further call blocks until one is waited for), so the host can overlap the PNG
+ * encode of frame k with the kernel and copy of frame k+1, and deal frames to one handle per GPU. `out` should be
+ * page-locked (rr_host_alloc); tickets must be waited for exactly once, on any thread. */
+int rr_render_rgb8_async(rr_scene *scene, const rr_frame_params *params, uint8_t *out, size_t row_stride,
+                         int32_t *ticket);
+int rr_render_wait(rr_scene *scene, int32_t ticket, float *kernel_ms);
+
 /* render(): unquantised RenderColor stream (r,g,b f32 per pixel, row-major) in HOST memory, for
  * callers whose pointproc is not the stock quantiser (generic `pointproc(x, y, &RenderColor)`). */
 int rr_render_f32(rr_scene *scene, const rr_frame_params *params, float *out_rgb);
@@ -217,10 +228,10 @@ int rr_render_rgb8_placed(rr_scene *scene, const rr_frame_params *params, uint8_
  * `epoch` into d_flags[params->band_index] (a uint32 array of band_count words in the FRAME OWNER's memory,
  * allocated with rr_device_alloc + rr_device_memset(0) and mapped by the other ranks like the frame) once all of
  * this shard's rows are in the frame: system-scope fence per block, last block does the release store
- * (ray-march mode: a one-thread publisher queued behind the render). The owner calls rr_fence_wait_device to make
+ * (both modes; an empty shard queues a one-thread publisher instead). The owner calls rr_fence_wait_device to make
  * its stream wait until all `count` words have reached `epoch` (acquire loads, bounded by timeout_ms; on timeout
  * *d_status is set to 1, d_status may be NULL). Epochs must grow from frame to frame. Both calls only enqueue work
- * (cuda_stream NULL = the default stream); signalled renders of one handle must be ordered on one stream.
+ * (cuda_stream NULL = the default stream); signalled renders of one shard must be ordered on one stream (epochs grow).
  * This replaces the channel receive loop of render.rs:871-886 across GPUs. */
 int rr_render_rgb8_placed_signal_device(rr_scene *scene, const rr_frame_params *params, void *d_frame,
                                         size_t row_stride, uint32_t *d_flags, uint32_t epoch,

@@ -7,7 +7,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -42,26 +44,41 @@ int fail_cuda(cudaError_t e, const char *what) {
 
 }  // namespace
 
-struct rr_scene {
-    int device = 0;
+// One in-flight host-facing render of a handle: its own stream pair, device frame and events. A handle owns RR_LANES of
+// them, so concurrent calls on one handle (the web server renders from several threads, webserver.rs:268-280) overlap on
+// the GPU instead of queueing behind one stream and one buffer, and rr_render_rgb8_async can keep several frames of an
+// animation in flight (render.rs:926-989).
+constexpr int RR_LANES = 4;
+struct Lane {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    void *d_out = nullptr;
+    size_t d_out_cap = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t chunk_ev[32] = {};
+    bool busy = false;      // taken by a call
+    bool pending = false;   // an async render is in flight on it (owned by its ticket)
+    uint32_t gen = 0;       // ticket generation
+};
+
+struct rr_scene {
+    int device = 0;
     rr::DevScene G{};
     rr::SceneHead H{};
     rr::LaunchInfo li{};
     std::vector<void *> allocs;
-    std::mutex mu;
-    void *d_out = nullptr;
-    size_t d_out_cap = 0;
+    std::mutex mu;               // guards lanes' busy flags, last_ms, culling
+    std::condition_variable cv;
+    Lane lanes[RR_LANES];
+    std::mutex cnt_mu;           // rr_render_count: one counter block per handle
     rr::Counters *d_cnt = nullptr;
-    unsigned *d_work = nullptr;  // word 0: march tile queue; words 16..79: 16 (work, done, -, -) slots of the trace kernel
-    unsigned launch_seq = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t chunk_ev[32] = {};
+    unsigned *d_work = nullptr;  // RR_SLOTS x (work, done, -, -): per-launch tile queue word + block counter
+    std::atomic<unsigned> launch_seq{0};
     float last_ms = 0.0f;
     bool timed = false;
     bool culling = true;
 };
+constexpr unsigned RR_SLOTS = 64;
 
 namespace {
 
@@ -120,19 +137,52 @@ rr::FrameParams to_dev(const rr_frame_params *p) {
 
 int launch(rr_scene *s, const rr::FrameParams &P, void *d_out, size_t row_stride, bool f32, rr::Counters *d_cnt,
            cudaStream_t st, unsigned *d_flag = nullptr, unsigned epoch = 0) {
-    // Each launch takes the next of 16 slots of (work, done) words: the trace kernel's tile queue and block counter reset
-    // themselves at the end of the launch, and kernels of one handle running concurrently on different streams never
-    // share a slot (unless more than 16 overlap). The trace kernel also publishes the completion signal itself (last
-    // block); march mode and empty shards fall back to a one-thread publisher queued behind the render on the same stream.
-    unsigned *slot = s->d_work + 16 + 4 * (s->launch_seq++ & 15u);
+    // Each launch takes the next of RR_SLOTS (work, done) word pairs: the kernels' tile queue and block counter reset
+    // themselves in the block that finishes last, so no memset is queued on the stream, and kernels of one handle running
+    // concurrently on different streams (ray-trace AND ray-march mode) never share a queue unless more than RR_SLOTS of
+    // them overlap. Both kernels publish the completion signal of a placed multi-GPU render themselves (last block); an
+    // empty shard falls back to a one-thread publisher queued on the same stream.
+    unsigned *slot = s->d_work + 4 * (s->launch_seq.fetch_add(1u, std::memory_order_relaxed) % RR_SLOTS);
     const rr::Signal sig{slot, slot + 1, d_flag, epoch};
-    const bool fused = d_flag && !P.use_raymarching && P.xres > 0 && P.local_rows > 0;
-    cudaError_t e = P.use_raymarching ? rr::launch_march(s->G, s->H, P, d_out, row_stride, f32, d_cnt, s->d_work, st, s->li, s->culling)
+    const bool fused = d_flag && P.xres > 0 && P.local_rows > 0;
+    cudaError_t e = P.use_raymarching ? rr::launch_march(s->G, s->H, P, d_out, row_stride, f32, d_cnt, sig, st, s->li, s->culling)
                                       : rr::launch_trace(s->G, s->H, P, d_out, row_stride, f32, d_cnt, st, s->li, s->culling, sig);
     if (e == cudaSuccess && d_flag && !fused) e = rr::launch_signal(sig, st);
     if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
     return RR_OK;
 }
+
+// ---- lanes --------------------------------------------------------------------------------------------------------
+Lane *acquire_lane(rr_scene *s) {
+    std::unique_lock<std::mutex> lk(s->mu);
+    for (;;) {
+        for (Lane &l : s->lanes)
+            if (!l.busy) { l.busy = true; return &l; }
+        s->cv.wait(lk);
+    }
+}
+void release_lane(rr_scene *s, Lane *l, float ms, bool timed) {
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        l->busy = false;
+        l->pending = false;
+        l->gen += 1;
+        if (timed) { s->last_ms = ms; s->timed = true; }
+    }
+    s->cv.notify_one();
+}
+// Scope guard of a blocking call: whatever way the call returns, nothing of it is still running on the lane's streams
+// (no DMA into the caller's buffer, no kernel reading d_out) when the lane goes back to the pool.
+struct LaneHold {
+    rr_scene *s; Lane *l; float ms = 0.0f; bool timed = false; bool keep = false;
+    LaneHold(rr_scene *s_) : s(s_), l(acquire_lane(s_)) {}
+    ~LaneHold() {
+        if (keep) return;  // handed over to an async ticket
+        if (!timed) { cudaStreamSynchronize(l->copy_stream); cudaStreamSynchronize(l->stream); cudaGetLastError(); }
+        release_lane(s, l, ms, timed);
+    }
+};
+
 
 using rr::Bvh;
 using rr::build_bvh;
@@ -197,15 +247,30 @@ bool mapped_host_alias(const void *host, size_t row_stride, void **dev) {
     return true;
 }
 
-int ensure_out(rr_scene *s, size_t bytes) {
-    if (bytes <= s->d_out_cap) return RR_OK;
-    if (s->d_out) cudaFree(s->d_out);
-    s->d_out = nullptr;
-    s->d_out_cap = 0;
-    CU(cudaMalloc(&s->d_out, bytes));
-    s->d_out_cap = bytes;
+int ensure_out(Lane *l, size_t bytes) {
+    if (bytes <= l->d_out_cap) return RR_OK;
+    if (l->d_out) cudaFree(l->d_out);
+    l->d_out = nullptr;
+    l->d_out_cap = 0;
+    CU(cudaMalloc(&l->d_out, bytes));
+    l->d_out_cap = bytes;
     return RR_OK;
 }
+
+// Timed launch on a lane: events around the launch(es), stream sync, elapsed ms into the hold.
+int finish_timed(LaneHold &h) {
+    CU(cudaStreamSynchronize(h.l->copy_stream));
+    CU(cudaStreamSynchronize(h.l->stream));
+    CU(cudaEventElapsedTime(&h.ms, h.l->ev0, h.l->ev1));
+    h.timed = true;
+    return RR_OK;
+}
+
+// Enqueue one host-bound RGB8 frame on a lane (everything rr_render_rgb8 does before it waits): either the kernel stores
+// straight into the caller's page-locked frame (long kernels) or the frame is rendered in row chunks on the lane's
+// stream with each chunk's device-to-host copy queued on the lane's copy stream behind its kernel.
+int enqueue_rgb8(rr_scene *s, Lane *l, const rr::FrameParams &P, uint8_t *out, size_t row_stride);
+
 
 }  // namespace
 
@@ -224,15 +289,20 @@ int rr_device_count(int *count) {
 int rr_scene_destroy(rr_scene *s) {
     if (!s) return RR_OK;
     cudaSetDevice(s->device);
-    if (s->stream) cudaStreamSynchronize(s->stream);
-    if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+    for (Lane &l : s->lanes) {
+        if (l.stream) cudaStreamSynchronize(l.stream);
+        if (l.copy_stream) cudaStreamSynchronize(l.copy_stream);
+    }
     for (void *p : s->allocs) cudaFree(p);
-    if (s->d_out) cudaFree(s->d_out);
-    if (s->ev0) cudaEventDestroy(s->ev0);
-    if (s->ev1) cudaEventDestroy(s->ev1);
-    for (auto &e : s->chunk_ev) if (e) cudaEventDestroy(e);
-    if (s->stream) cudaStreamDestroy(s->stream);
-    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    for (Lane &l : s->lanes) {
+        if (l.d_out) cudaFree(l.d_out);
+        if (l.ev0) cudaEventDestroy(l.ev0);
+        if (l.ev1) cudaEventDestroy(l.ev1);
+        for (auto &e : l.chunk_ev) if (e) cudaEventDestroy(e);
+        if (l.stream) cudaStreamDestroy(l.stream);
+        if (l.copy_stream) cudaStreamDestroy(l.copy_stream);
+    }
+    cudaGetLastError();
     delete s;
     return RR_OK;
 }
@@ -369,18 +439,21 @@ int rr_scene_create(const rr_scene_desc *desc, int device, rr_scene **out) {
     int sm = 0, optin = 0;
     if ((e = cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaEventCreate(&s->ev0)) != cudaSuccess || (e = cudaEventCreate(&s->ev1)) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void **>(&s->d_cnt), sizeof(rr::Counters))) != cudaSuccess ||
-        (e = cudaMalloc(reinterpret_cast<void **>(&s->d_work), 512)) != cudaSuccess)
+        (e = cudaMalloc(reinterpret_cast<void **>(&s->d_work), RR_SLOTS * 4 * sizeof(unsigned))) != cudaSuccess)
         return bail(fail_cuda(e, "rr_scene_create"));
     s->allocs.push_back(s->d_cnt);
     s->allocs.push_back(s->d_work);
-    if ((e = cudaMemset(s->d_work, 0, 512)) != cudaSuccess) return bail(fail_cuda(e, "cudaMemset"));
+    if ((e = cudaMemset(s->d_work, 0, RR_SLOTS * 4 * sizeof(unsigned))) != cudaSuccess) return bail(fail_cuda(e, "cudaMemset"));
     if ((e = rr::preload_signal_kernels()) != cudaSuccess) return bail(fail_cuda(e, "preload"));
-    for (auto &ev : s->chunk_ev)
-        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
+    for (Lane &l : s->lanes) {
+        if ((e = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&l.copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreate(&l.ev0)) != cudaSuccess || (e = cudaEventCreate(&l.ev1)) != cudaSuccess)
+            return bail(fail_cuda(e, "rr_scene_create"));
+        for (auto &ev : l.chunk_ev)
+            if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
+    }
     s->li.sm_count = sm;
     s->li.smem_optin = (size_t)optin;
     *out = s;
@@ -395,91 +468,143 @@ int rr_frame_rows(const rr_frame_params *params, int32_t *rows_out) {
     return RR_OK;
 }
 
+// Device-resident render on a caller stream: only the launch is enqueued, nothing of the handle is held afterwards, so
+// any number of such launches may be in flight on different streams (each has its own queue slot, see launch()).
+// cuda_stream == NULL: one of the handle's lanes, timed, synchronous.
+static int render_device(rr_scene *s, rr::FrameParams &P, void *d_out, size_t row_stride, bool f32, void *cuda_stream,
+                         unsigned *d_flag = nullptr, unsigned epoch = 0) {
+    CU(cudaSetDevice(s->device));
+    if (cuda_stream) return launch(s, P, d_out, row_stride, f32, nullptr, reinterpret_cast<cudaStream_t>(cuda_stream), d_flag, epoch);
+    LaneHold h(s);
+    int rc;
+    CU(cudaEventRecord(h.l->ev0, h.l->stream));
+    if ((rc = launch(s, P, d_out, row_stride, f32, nullptr, h.l->stream, d_flag, epoch))) return rc;
+    CU(cudaEventRecord(h.l->ev1, h.l->stream));
+    return finish_timed(h);
+}
+
 int rr_render_rgb8_device(rr_scene *s, const rr_frame_params *params, void *d_out, size_t row_stride, void *cuda_stream) {
     if (!s || !d_out) return fail(RR_ERR_BAD_ARG, "scene/d_out is null");
     int rc = check_params(params);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(s->mu);
-    CU(cudaSetDevice(s->device));
     rr::FrameParams P = to_dev(params);
     if (row_stride == 0) row_stride = (size_t)P.xres * 3;
     if (row_stride < (size_t)P.xres * 3) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
-    if (cuda_stream) return launch(s, P, d_out, row_stride, false, nullptr, reinterpret_cast<cudaStream_t>(cuda_stream));
-    CU(cudaEventRecord(s->ev0, s->stream));
-    if ((rc = launch(s, P, d_out, row_stride, false, nullptr, s->stream))) return rc;
-    CU(cudaEventRecord(s->ev1, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
-    CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
-    s->timed = true;
-    return RR_OK;
+    return render_device(s, P, d_out, row_stride, false, cuda_stream);
 }
 
 int rr_render_f32_device(rr_scene *s, const rr_frame_params *params, void *d_out, void *cuda_stream) {
     if (!s || !d_out) return fail(RR_ERR_BAD_ARG, "scene/d_out is null");
     int rc = check_params(params);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(s->mu);
-    CU(cudaSetDevice(s->device));
     rr::FrameParams P = to_dev(params);
-    if (cuda_stream) return launch(s, P, d_out, 0, true, nullptr, reinterpret_cast<cudaStream_t>(cuda_stream));
-    CU(cudaEventRecord(s->ev0, s->stream));
-    if ((rc = launch(s, P, d_out, 0, true, nullptr, s->stream))) return rc;
-    CU(cudaEventRecord(s->ev1, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
-    CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
-    s->timed = true;
-    return RR_OK;
+    return render_device(s, P, d_out, 0, true, cuda_stream);
 }
 
-// Frame to host memory. The frame is rendered in up to 8 row chunks on the handle's stream; each
-// chunk's device-to-host copy is queued on a second stream as soon as its kernel finishes, so the
-// PCIe transfer of chunk k overlaps the kernel of chunk k+1 (the copy is the longer leg at 4K/8K).
-int rr_render_rgb8(rr_scene *s, const rr_frame_params *params, uint8_t *out, size_t row_stride) {
-    if (!s || !out) return fail(RR_ERR_BAD_ARG, "scene/out is null");
-    int rc = check_params(params);
-    if (rc) return rc;
-    std::lock_guard<std::mutex> lk(s->mu);
-    CU(cudaSetDevice(s->device));
-    rr::FrameParams P = to_dev(params);
+}  // extern "C"
+
+namespace {
+int enqueue_rgb8(rr_scene *s, Lane *l, const rr::FrameParams &P, uint8_t *out, size_t row_stride) {
+    int rc;
     const size_t packed = (size_t)P.xres * 3;
-    if (row_stride == 0) row_stride = packed;
-    if (row_stride < packed) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
     const int rows = P.local_rows;
-    if (rows == 0 || P.xres == 0) return RR_OK;
     void *alias = nullptr;
     if (long_kernel(P, s) && P.xres % 8 == 0 && mapped_host_alias(out, row_stride, &alias)) {
-        CU(cudaEventRecord(s->ev0, s->stream));
-        if ((rc = launch(s, P, alias, row_stride, false, nullptr, s->stream))) return rc;
-        CU(cudaEventRecord(s->ev1, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
-        CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
-        s->timed = true;
+        CU(cudaEventRecord(l->ev0, l->stream));
+        if ((rc = launch(s, P, alias, row_stride, false, nullptr, l->stream))) return rc;
+        CU(cudaEventRecord(l->ev1, l->stream));
         return RR_OK;
     }
-    if ((rc = ensure_out(s, packed * rows))) return rc;
+    if ((rc = ensure_out(l, packed * rows))) return rc;
     const int nchunk = pick_chunks(packed * rows, P, s);
     int plan[32];
     const int nplan = plan_chunks(rows, nchunk, plan);
-    CU(cudaEventRecord(s->ev0, s->stream));
+    CU(cudaEventRecord(l->ev0, l->stream));
     for (int k = 0, r0 = 0; k < nplan; r0 += plan[k], ++k) {
         rr::FrameParams C = P;
         C.row0 = r0;
         C.local_rows = plan[k];
-        uint8_t *d = reinterpret_cast<uint8_t *>(s->d_out) + (size_t)r0 * packed;
-        if ((rc = launch(s, C, d, packed, false, nullptr, s->stream))) return rc;
-        CU(cudaEventRecord(s->chunk_ev[k], s->stream));
-        CU(cudaStreamWaitEvent(s->copy_stream, s->chunk_ev[k], 0));
+        uint8_t *d = reinterpret_cast<uint8_t *>(l->d_out) + (size_t)r0 * packed;
+        if ((rc = launch(s, C, d, packed, false, nullptr, l->stream))) return rc;
+        CU(cudaEventRecord(l->chunk_ev[k], l->stream));
+        CU(cudaStreamWaitEvent(l->copy_stream, l->chunk_ev[k], 0));
         if (row_stride == packed)  // contiguous rows: plain 1-D copy
-            CU(cudaMemcpyAsync(out + (size_t)r0 * packed, d, packed * (size_t)C.local_rows, cudaMemcpyDeviceToHost, s->copy_stream));
+            CU(cudaMemcpyAsync(out + (size_t)r0 * packed, d, packed * (size_t)C.local_rows, cudaMemcpyDeviceToHost, l->copy_stream));
         else
             CU(cudaMemcpy2DAsync(out + (size_t)r0 * row_stride, row_stride, d, packed, packed, (size_t)C.local_rows,
-                                 cudaMemcpyDeviceToHost, s->copy_stream));
+                                 cudaMemcpyDeviceToHost, l->copy_stream));
     }
-    CU(cudaEventRecord(s->ev1, s->stream));
-    CU(cudaStreamSynchronize(s->copy_stream));
-    CU(cudaStreamSynchronize(s->stream));
-    CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
-    s->timed = true;
+    CU(cudaEventRecord(l->ev1, l->stream));
+    return RR_OK;
+}
+}  // namespace
+
+extern "C" {
+
+// Frame to host memory. Short kernels: the frame is rendered in up to 32 row chunks (geometric plan, plan_chunks) on a
+// lane's stream; each chunk's device-to-host copy is queued on the lane's second stream as soon as its kernel finishes,
+// so the PCIe transfer of chunk k overlaps the kernel of chunk k+1 (the copy is the longer leg at 4K/8K).
+int rr_render_rgb8(rr_scene *s, const rr_frame_params *params, uint8_t *out, size_t row_stride) {
+    if (!s || !out) return fail(RR_ERR_BAD_ARG, "scene/out is null");
+    int rc = check_params(params);
+    if (rc) return rc;
+    rr::FrameParams P = to_dev(params);
+    const size_t packed = (size_t)P.xres * 3;
+    if (row_stride == 0) row_stride = packed;
+    if (row_stride < packed) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
+    if (P.local_rows == 0 || P.xres == 0) return RR_OK;
+    CU(cudaSetDevice(s->device));
+    LaneHold h(s);
+    if ((rc = enqueue_rgb8(s, h.l, P, out, row_stride))) return rc;
+    return finish_timed(h);
+}
+
+// render_frames support (render.rs:926-989: many frames of one scene): the same frame-to-host pipeline, but the call
+// returns as soon as everything is queued. Up to RR_LANES frames of one handle can be in flight; a further call waits
+// for a free lane. `out` should be page-locked (rr_host_alloc) for the copies to be asynchronous.
+int rr_render_rgb8_async(rr_scene *s, const rr_frame_params *params, uint8_t *out, size_t row_stride, int32_t *ticket) {
+    if (!s || !out || !ticket) return fail(RR_ERR_BAD_ARG, "scene/out/ticket is null");
+    *ticket = -1;
+    int rc = check_params(params);
+    if (rc) return rc;
+    rr::FrameParams P = to_dev(params);
+    const size_t packed = (size_t)P.xres * 3;
+    if (row_stride == 0) row_stride = packed;
+    if (row_stride < packed) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
+    CU(cudaSetDevice(s->device));
+    LaneHold h(s);
+    if (P.local_rows > 0 && P.xres > 0) {
+        if ((rc = enqueue_rgb8(s, h.l, P, out, row_stride))) return rc;
+    } else {
+        CU(cudaEventRecord(h.l->ev0, h.l->stream));
+        CU(cudaEventRecord(h.l->ev1, h.l->stream));
+    }
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        h.l->pending = true;
+        *ticket = (int32_t)((h.l - s->lanes) | (int)((h.l->gen & 0xffffffu) << 4));
+    }
+    h.keep = true;
+    return RR_OK;
+}
+
+int rr_render_wait(rr_scene *s, int32_t ticket, float *kernel_ms) {
+    if (!s || ticket < 0) return fail(RR_ERR_BAD_ARG, "scene is null or bad ticket");
+    const int li = ticket & 15;
+    if (li >= RR_LANES) return fail(RR_ERR_BAD_ARG, "bad ticket");
+    Lane *l = &s->lanes[li];
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (!l->busy || !l->pending || (int)((l->gen & 0xffffffu) << 4 | li) != ticket) return fail(RR_ERR_BAD_ARG, "stale ticket");
+    }
+    CU(cudaSetDevice(s->device));
+    cudaError_t e1 = cudaStreamSynchronize(l->copy_stream), e2 = cudaStreamSynchronize(l->stream);
+    float ms = 0.0f;
+    cudaError_t e3 = (e1 == cudaSuccess && e2 == cudaSuccess) ? cudaEventElapsedTime(&ms, l->ev0, l->ev1) : cudaSuccess;
+    const bool ok = e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess;
+    release_lane(s, l, ms, ok);
+    if (!ok) return fail_cuda(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3), "rr_render_wait");
+    if (kernel_ms) *kernel_ms = ms;
     return RR_OK;
 }
 
@@ -487,45 +612,44 @@ int rr_render_f32(rr_scene *s, const rr_frame_params *params, float *out_rgb) {
     if (!s || !out_rgb) return fail(RR_ERR_BAD_ARG, "scene/out is null");
     int rc = check_params(params);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(s->mu);
-    CU(cudaSetDevice(s->device));
     rr::FrameParams P = to_dev(params);
     const size_t bytes = (size_t)P.xres * P.local_rows * 3 * sizeof(float);
     if (bytes == 0) return RR_OK;
-    if ((rc = ensure_out(s, bytes))) return rc;
-    CU(cudaEventRecord(s->ev0, s->stream));
-    if ((rc = launch(s, P, s->d_out, 0, true, nullptr, s->stream))) return rc;
-    CU(cudaEventRecord(s->ev1, s->stream));
-    CU(cudaMemcpyAsync(out_rgb, s->d_out, bytes, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
-    CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
-    s->timed = true;
-    return RR_OK;
+    CU(cudaSetDevice(s->device));
+    LaneHold h(s);
+    if ((rc = ensure_out(h.l, bytes))) return rc;
+    CU(cudaEventRecord(h.l->ev0, h.l->stream));
+    if ((rc = launch(s, P, h.l->d_out, 0, true, nullptr, h.l->stream))) return rc;
+    CU(cudaEventRecord(h.l->ev1, h.l->stream));
+    CU(cudaMemcpyAsync(out_rgb, h.l->d_out, bytes, cudaMemcpyDeviceToHost, h.l->stream));
+    return finish_timed(h);
 }
 
 int rr_render_count(rr_scene *s, const rr_frame_params *params, uint8_t *out, size_t row_stride, rr_ray_counts *counts) {
     if (!s || !counts) return fail(RR_ERR_BAD_ARG, "scene/counts is null");
     int rc = check_params(params);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(s->mu);
-    CU(cudaSetDevice(s->device));
     rr::FrameParams P = to_dev(params);
     const size_t packed = (size_t)P.xres * 3;
     if (row_stride == 0) row_stride = packed;
     if (row_stride < packed) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
     std::memset(counts, 0, sizeof(*counts));
     if (P.local_rows == 0 || P.xres == 0) return RR_OK;
-    if ((rc = ensure_out(s, packed * P.local_rows))) return rc;
-    CU(cudaMemsetAsync(s->d_cnt, 0, sizeof(rr::Counters), s->stream));
-    if ((rc = launch(s, P, s->d_out, packed, false, s->d_cnt, s->stream))) return rc;
-    rr::Counters h{};
-    CU(cudaMemcpyAsync(&h, s->d_cnt, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaSetDevice(s->device));
+    std::lock_guard<std::mutex> ck(s->cnt_mu);  // one counter block per handle
+    LaneHold h(s);
+    cudaStream_t st = h.l->stream;
+    if ((rc = ensure_out(h.l, packed * P.local_rows))) return rc;
+    CU(cudaMemsetAsync(s->d_cnt, 0, sizeof(rr::Counters), st));
+    if ((rc = launch(s, P, h.l->d_out, packed, false, s->d_cnt, st))) return rc;
+    rr::Counters c{};
+    CU(cudaMemcpyAsync(&c, s->d_cnt, sizeof(c), cudaMemcpyDeviceToHost, st));
     if (out)
-        CU(cudaMemcpy2DAsync(out, row_stride, s->d_out, packed, packed, (size_t)P.local_rows, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
-    counts->pixels = h.pixels; counts->primary = h.primary; counts->reflect = h.reflect; counts->refract = h.refract;
-    counts->shadow = h.shadow; counts->object_tests = h.object_tests; counts->march_steps = h.march_steps;
-    counts->bg_evals = h.bg_evals; counts->sphere_tests = h.sphere_tests; counts->sphere_hits = h.sphere_hits;
+        CU(cudaMemcpy2DAsync(out, row_stride, h.l->d_out, packed, packed, (size_t)P.local_rows, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    counts->pixels = c.pixels; counts->primary = c.primary; counts->reflect = c.reflect; counts->refract = c.refract;
+    counts->shadow = c.shadow; counts->object_tests = c.object_tests; counts->march_steps = c.march_steps;
+    counts->bg_evals = c.bg_evals; counts->sphere_tests = c.sphere_tests; counts->sphere_hits = c.sphere_hits;
     return RR_OK;
 }
 
@@ -546,20 +670,11 @@ int rr_render_rgb8_placed_device(rr_scene *s, const rr_frame_params *params, voi
     if (!s || !d_frame) return fail(RR_ERR_BAD_ARG, "scene/d_frame is null");
     int rc = check_params(params);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(s->mu);
-    CU(cudaSetDevice(s->device));
     rr::FrameParams P = to_dev(params);
     P.placed = 1;
     if (row_stride == 0) row_stride = (size_t)P.xres * 3;
     if (row_stride < (size_t)P.xres * 3) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
-    if (cuda_stream) return launch(s, P, d_frame, row_stride, false, nullptr, reinterpret_cast<cudaStream_t>(cuda_stream));
-    CU(cudaEventRecord(s->ev0, s->stream));
-    if ((rc = launch(s, P, d_frame, row_stride, false, nullptr, s->stream))) return rc;
-    CU(cudaEventRecord(s->ev1, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
-    CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
-    s->timed = true;
-    return RR_OK;
+    return render_device(s, P, d_frame, row_stride, false, cuda_stream);
 }
 
 // Same render, plus the completion signal carried by the kernel (rr_device.cuh Signal): epoch lands in
@@ -569,12 +684,11 @@ int rr_render_rgb8_placed_signal_device(rr_scene *s, const rr_frame_params *para
     if (!s || !d_frame || !d_flags) return fail(RR_ERR_BAD_ARG, "scene/d_frame/d_flags is null");
     int rc = check_params(params);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(s->mu);
-    CU(cudaSetDevice(s->device));
     rr::FrameParams P = to_dev(params);
     P.placed = 1;
     if (row_stride == 0) row_stride = (size_t)P.xres * 3;
     if (row_stride < (size_t)P.xres * 3) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
+    CU(cudaSetDevice(s->device));
     return launch(s, P, d_frame, row_stride, false, nullptr, reinterpret_cast<cudaStream_t>(cuda_stream), d_flags + P.band_index, epoch);
 }
 
@@ -614,7 +728,6 @@ int rr_render_rgb8_placed(rr_scene *s, const rr_frame_params *params, uint8_t *h
     if (!s || !host_frame) return fail(RR_ERR_BAD_ARG, "scene/host_frame is null");
     int rc = check_params(params);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaSetDevice(s->device));
     rr::FrameParams P = to_dev(params);
     const size_t packed = (size_t)P.xres * 3;
@@ -622,40 +735,39 @@ int rr_render_rgb8_placed(rr_scene *s, const rr_frame_params *params, uint8_t *h
     if (row_stride < packed) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
     const int rows = P.local_rows;
     if (rows == 0 || P.xres == 0) return RR_OK;
+    LaneHold h(s);
+    Lane *l = h.l;
     void *alias = nullptr;
     if (long_kernel(P, s) && P.xres % 8 == 0 && mapped_host_alias(host_frame, row_stride, &alias)) {
         rr::FrameParams Z = P;
         Z.placed = 1;  // rows go to their image position in the (shared) host frame
-        CU(cudaEventRecord(s->ev0, s->stream));
-        if ((rc = launch(s, Z, alias, row_stride, false, nullptr, s->stream))) return rc;
-        CU(cudaEventRecord(s->ev1, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
-        CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
-        s->timed = true;
-        return RR_OK;
+        CU(cudaEventRecord(l->ev0, l->stream));
+        if ((rc = launch(s, Z, alias, row_stride, false, nullptr, l->stream))) return rc;
+        CU(cudaEventRecord(l->ev1, l->stream));
+        return finish_timed(h);
     }
-    if ((rc = ensure_out(s, packed * rows))) return rc;
+    if ((rc = ensure_out(l, packed * rows))) return rc;
     const int B = P.band_count <= 1 ? 4 : P.band_rows, n = P.band_count, k = P.band_index;
-    // Same pipeline as rr_render_rgb8: up to 8 chunks of whole bands, each chunk's device-to-host copy
+    // Same pipeline as rr_render_rgb8: up to 16 chunks of whole bands, each chunk's device-to-host copy
     // queued on the copy stream behind its kernel so PCIe overlaps the next chunk's rendering.
     const int nchunk = pick_chunks(packed * rows, P, s);
     int chunk_rows = (rows + nchunk - 1) / nchunk;
     const int align = (B % 4 == 0) ? B : B * 4;  // whole bands and whole 4-row tiles
     chunk_rows = ((chunk_rows + align - 1) / align) * align;
-    CU(cudaEventRecord(s->ev0, s->stream));
+    CU(cudaEventRecord(l->ev0, l->stream));
     int ci = 0;
     for (int r0 = 0; r0 < rows; r0 += chunk_rows, ++ci) {
         rr::FrameParams Cp = P;
         Cp.row0 = r0;
         Cp.local_rows = rows - r0 < chunk_rows ? rows - r0 : chunk_rows;
-        uint8_t *d = reinterpret_cast<uint8_t *>(s->d_out) + (size_t)r0 * packed;
-        if ((rc = launch(s, Cp, d, packed, false, nullptr, s->stream))) return rc;
-        CU(cudaEventRecord(s->chunk_ev[ci], s->stream));
-        CU(cudaStreamWaitEvent(s->copy_stream, s->chunk_ev[ci], 0));
+        uint8_t *d = reinterpret_cast<uint8_t *>(l->d_out) + (size_t)r0 * packed;
+        if ((rc = launch(s, Cp, d, packed, false, nullptr, l->stream))) return rc;
+        CU(cudaEventRecord(l->chunk_ev[ci], l->stream));
+        CU(cudaStreamWaitEvent(l->copy_stream, l->chunk_ev[ci], 0));
         const int nr = Cp.local_rows;
         if (n <= 1) {
             CU(cudaMemcpy2DAsync(host_frame + (size_t)r0 * row_stride, row_stride, d, packed, packed, (size_t)nr,
-                                 cudaMemcpyDeviceToHost, s->copy_stream));
+                                 cudaMemcpyDeviceToHost, l->copy_stream));
         } else if (row_stride == packed) {
             // a band is B contiguous rows; this shard's bands are n*B rows apart in the frame: one strided copy
             const int full = nr / B, tail = nr - full * B;
@@ -663,25 +775,21 @@ int rr_render_rgb8_placed(rr_scene *s, const rr_frame_params *params, uint8_t *h
             const size_t first_band = (size_t)(r0 / B);
             if (full > 0)
                 CU(cudaMemcpy2DAsync(host_frame + (first_band * n + k) * band_bytes, (size_t)n * band_bytes, d, band_bytes, band_bytes,
-                                     (size_t)full, cudaMemcpyDeviceToHost, s->copy_stream));
+                                     (size_t)full, cudaMemcpyDeviceToHost, l->copy_stream));
             if (tail > 0)
                 CU(cudaMemcpyAsync(host_frame + ((first_band + full) * n + k) * band_bytes, d + (size_t)full * band_bytes,
-                                   (size_t)tail * packed, cudaMemcpyDeviceToHost, s->copy_stream));
+                                   (size_t)tail * packed, cudaMemcpyDeviceToHost, l->copy_stream));
         } else {
             for (int b0 = 0; b0 < nr; b0 += B) {  // padded rows: one 2D copy per band
                 const int br = nr - b0 < B ? nr - b0 : B;
                 const size_t iy = ((size_t)((r0 + b0) / B) * n + k) * B;
                 CU(cudaMemcpy2DAsync(host_frame + iy * row_stride, row_stride, d + (size_t)b0 * packed, packed, packed, (size_t)br,
-                                     cudaMemcpyDeviceToHost, s->copy_stream));
+                                     cudaMemcpyDeviceToHost, l->copy_stream));
             }
         }
     }
-    CU(cudaEventRecord(s->ev1, s->stream));
-    CU(cudaStreamSynchronize(s->copy_stream));
-    CU(cudaStreamSynchronize(s->stream));
-    CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
-    s->timed = true;
-    return RR_OK;
+    CU(cudaEventRecord(l->ev1, l->stream));
+    return finish_timed(h);
 }
 
 int rr_device_alloc(int device, size_t bytes, void **d_ptr) {

@@ -18,9 +18,10 @@ struct LaunchInfo {
 // d_cnt != nullptr selects the instrumented instantiation.
 cudaError_t launch_trace(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
                          Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh, const Signal &sig = Signal{nullptr, nullptr, nullptr, 0u});
-// Ray-march mode (same contract). d_work: one unsigned int work counter (zeroed by the launcher).
+// Ray-march mode (same contract). sig.work / sig.done: this launch's tile-queue word and block counter (both zero at
+// launch; the last block resets them), sig.flag: optional completion word, as for the trace kernel.
 cudaError_t launch_march(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
-                         Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh = true);
+                         Counters *d_cnt, const Signal &sig, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh = true);
 // Row-band un-interleave (multi-GPU gather epilogue).
 cudaError_t launch_bands_unpack(const FrameParams &P, const void *d_packed, size_t shard_stride, void *d_frame,
                                 cudaStream_t stream);

@@ -51,7 +51,7 @@ __device__ __forceinline__ MarchView stage_march(const DevScene &G, float4 *smem
 template <bool COUNT, bool F32OUT, bool STAGE, int GLOW, bool MBVH>
 __global__ void __launch_bounds__(MARCH_THREADS)
 march_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHead H, const __grid_constant__ FrameParams P,
-             void *__restrict__ out, size_t row_stride, Counters *gcnt, unsigned *work, int fast_store) {
+             void *__restrict__ out, size_t row_stride, Counters *gcnt, int fast_store, const Signal sig) {
     extern __shared__ float4 rr_smem[];
     const MarchView S = stage_march(G, rr_smem, STAGE);
 
@@ -64,7 +64,7 @@ march_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
 
     for (;;) {
         int tile = 0;
-        if (lane == 0) tile = (int)atomicAdd(work, 1u);
+        if (lane == 0) tile = (int)atomicAdd(sig.work, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= ntiles) break;
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
@@ -85,6 +85,10 @@ march_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
         }
     }
     if (COUNT) flush_counters(cnt, gcnt);
+    // Like the trace kernel: the block that finishes last resets the launch's queue word and block counter (so the slot
+    // is clean for its next use without a memset on the stream) and, for placed multi-GPU frames, publishes the
+    // completion word in the frame owner's memory.
+    finish_launch(sig);
 }
 
 static size_t march_smem_bytes(const DevScene &G) {
@@ -95,7 +99,7 @@ static size_t march_smem_bytes(const DevScene &G) {
 
 template <bool COUNT, bool F32OUT, bool STAGE, int GLOW, bool MBVH = false>
 static cudaError_t launch_one(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
-                              Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li, size_t smem) {
+                              Counters *d_cnt, const Signal &sig, cudaStream_t stream, const LaunchInfo &li, size_t smem) {
     auto kern = march_kernel<COUNT, F32OUT, STAGE, GLOW, MBVH>;
     cudaError_t e;
     if (smem > 48 * 1024) {
@@ -111,16 +115,14 @@ static cudaError_t launch_one(const DevScene &G, const SceneHead &H, const Frame
     long long grid = (long long)li.sm_count * per_sm;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    e = cudaMemsetAsync(d_work, 0, sizeof(unsigned), stream);
-    if (e != cudaSuccess) return e;
     const int fast = (!F32OUT && (P.xres % 8 == 0) && (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0)) ? 1 : 0;
-    kern<<<(unsigned)grid, MARCH_THREADS, smem, stream>>>(G, H, P, d_out, row_stride, d_cnt, d_work, fast);
+    kern<<<(unsigned)grid, MARCH_THREADS, smem, stream>>>(G, H, P, d_out, row_stride, d_cnt, fast, sig);
     return cudaGetLastError();
 }
 
 template <bool COUNT, bool F32OUT>
 static cudaError_t launch_two(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
-                              Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh) {
+                              Counters *d_cnt, const Signal &sig, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh) {
     size_t smem = march_smem_bytes(G);
     const bool stage = smem <= li.smem_optin / 2;
     if (!stage) smem = 0;
@@ -130,26 +132,26 @@ static cudaError_t launch_two(const DevScene &G, const SceneHead &H, const Frame
     // Large scenes: the sphere scan goes through the BVH (rr_march.cuh, MBVH); nothing is staged (floor tails and BVH are
     // read through L1). Inline glow keeps the linear scan.
     if (allow_bvh && G.n_bvh_nodes > 0 && glow != 2) {
-        if (glow == 0) return launch_one<COUNT, F32OUT, false, 0, true>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, 0);
-        return launch_one<COUNT, F32OUT, false, 1, true>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, 0);
+        if (glow == 0) return launch_one<COUNT, F32OUT, false, 0, true>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, 0);
+        return launch_one<COUNT, F32OUT, false, 1, true>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, 0);
     }
     if (stage) {
-        if (glow == 0) return launch_one<COUNT, F32OUT, true, 0>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, smem);
-        if (glow == 1) return launch_one<COUNT, F32OUT, true, 1>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, smem);
-        return launch_one<COUNT, F32OUT, true, 2>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, smem);
+        if (glow == 0) return launch_one<COUNT, F32OUT, true, 0>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem);
+        if (glow == 1) return launch_one<COUNT, F32OUT, true, 1>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem);
+        return launch_one<COUNT, F32OUT, true, 2>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem);
     }
-    if (glow == 0) return launch_one<COUNT, F32OUT, false, 0>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, smem);
-    if (glow == 1) return launch_one<COUNT, F32OUT, false, 1>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, smem);
-    return launch_one<COUNT, F32OUT, false, 2>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, smem);
+    if (glow == 0) return launch_one<COUNT, F32OUT, false, 0>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem);
+    if (glow == 1) return launch_one<COUNT, F32OUT, false, 1>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem);
+    return launch_one<COUNT, F32OUT, false, 2>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem);
 }
 
 cudaError_t launch_march(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
-                         bool f32_out, Counters *d_cnt, unsigned *d_work, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh) {
+                         bool f32_out, Counters *d_cnt, const Signal &sig, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh) {
     if (P.xres <= 0 || P.local_rows <= 0) return cudaSuccess;
-    if (d_cnt) return f32_out ? launch_two<true, true>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, allow_bvh)
-                              : launch_two<true, false>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, allow_bvh);
-    return f32_out ? launch_two<false, true>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, allow_bvh)
-                   : launch_two<false, false>(G, H, P, d_out, row_stride, d_cnt, d_work, stream, li, allow_bvh);
+    if (d_cnt) return f32_out ? launch_two<true, true>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, allow_bvh)
+                              : launch_two<true, false>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, allow_bvh);
+    return f32_out ? launch_two<false, true>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, allow_bvh)
+                   : launch_two<false, false>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, allow_bvh);
 }
 
 }  // namespace rr

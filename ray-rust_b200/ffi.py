@@ -121,6 +121,8 @@ PROTOTYPES = {
     "rr_scene_set_culling": (C.c_int, [_P, C.c_int]),
     "rr_frame_rows": (C.c_int, [C.POINTER(rr_frame_params), C.POINTER(C.c_int32)]),
     "rr_render_rgb8": (C.c_int, [_P, C.POINTER(rr_frame_params), _P, C.c_size_t]),
+    "rr_render_rgb8_async": (C.c_int, [_P, C.POINTER(rr_frame_params), _P, C.c_size_t, C.POINTER(C.c_int32)]),
+    "rr_render_wait": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float)]),
     "rr_render_f32": (C.c_int, [_P, C.POINTER(rr_frame_params), _P]),
     "rr_render_rgb8_device": (C.c_int, [_P, C.POINTER(rr_frame_params), _P, C.c_size_t, _P]),
     "rr_render_f32_device": (C.c_int, [_P, C.POINTER(rr_frame_params), _P, _P]),

@@ -150,6 +150,10 @@ typedef struct rr_scene rr_scene; /* opaque: device-resident flattened scene + p
 /* ABI version of the loaded library (== RR_ABI_VERSION). */
 int rr_abi_version(void);
 
+/* "rr_src_hash=<hex> arch=sm_100a fmad=false": the content hash of the sources and compiler flags this binary was built
+ * from. Bindings compare it with the sources they sit next to and refuse (or rebuild) a stale binary. */
+const char *rr_build_info(void);
+
 /* Thread-local message of the last failure on this thread ("" if none). Never NULL. */
 const char *rr_last_error(void);
 

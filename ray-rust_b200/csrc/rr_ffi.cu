@@ -119,7 +119,7 @@ int check_params(const rr_frame_params *p) {
     return RR_OK;
 }
 
-rr::FrameParams to_dev(const rr_frame_params *p) {
+rr::FrameParams to_dev(const rr_frame_params *p, const rr_scene *s) {
     rr::FrameParams d{};
     d.xres = p->xres; d.yres = p->yres; d.xfov = p->xfov; d.yfov = p->yfov;
     for (int k = 0; k < 3; ++k) { d.cam_pos[k] = p->cam_position[k]; d.light[k] = p->light[k]; }
@@ -132,6 +132,7 @@ rr::FrameParams to_dev(const rr_frame_params *p) {
     d.band_index = d.band_count == 1 ? 0 : p->band_index;
     d.local_rows = rows_of(p);
     d.row0 = 0;
+    if (s) rr::finish_frame_params(d, s->H);
     return d;
 }
 
@@ -278,6 +279,12 @@ extern "C" {
 
 int rr_abi_version(void) { return RR_ABI_VERSION; }
 
+#ifndef RR_SRC_HASH
+#define RR_SRC_HASH "unknown"
+#endif
+// "rr_src_hash=<sha256/32 of the sources and flags this binary was built from>": read back by build.py / ffi.py
+const char *rr_build_info(void) { return "rr_src_hash=" RR_SRC_HASH " arch=sm_100a fmad=false"; }
+
 const char *rr_last_error(void) { return g_last_error.c_str(); }
 
 int rr_device_count(int *count) {
@@ -313,6 +320,7 @@ int rr_scene_create(const rr_scene_desc *desc, int device, rr_scene **out) {
     if (desc->n_objects && !desc->objects) return fail(RR_ERR_BAD_ARG, "objects is null");
     if (desc->n_materials && !desc->materials) return fail(RR_ERR_BAD_ARG, "materials is null");
     if (desc->n_textures && !desc->textures) return fail(RR_ERR_BAD_ARG, "textures is null");
+    if (desc->n_objects >= (1u << 22)) return fail(RR_ERR_UNSUPPORTED, "more than 2^22 objects (object index field of the device recursion stack)");
     // validate indices and enums before touching the device
     for (uint32_t i = 0; i < desc->n_materials; ++i) {
         const rr_material &m = desc->materials[i];
@@ -434,6 +442,7 @@ int rr_scene_create(const rr_scene_desc *desc, int device, rr_scene **out) {
     for (int k = 0; k < rr::RR_HEAD_FLOORS && k < (int)flo_o.size(); ++k) {
         s->H.flo_o[k] = flo_o[k]; s->H.flo_n[k] = flo_n[k]; s->H.flo_oi[k] = flo_oi[k];
     }
+    rr::fill_head_pairs(s->H, std::min((int)sph.size(), rr::RR_HEAD_SPHERES), std::min((int)flo_o.size(), rr::RR_HEAD_FLOORS));
 
     cudaError_t e;
     int sm = 0, optin = 0;
@@ -487,7 +496,7 @@ int rr_render_rgb8_device(rr_scene *s, const rr_frame_params *params, void *d_ou
     if (!s || !d_out) return fail(RR_ERR_BAD_ARG, "scene/d_out is null");
     int rc = check_params(params);
     if (rc) return rc;
-    rr::FrameParams P = to_dev(params);
+    rr::FrameParams P = to_dev(params, s);
     if (row_stride == 0) row_stride = (size_t)P.xres * 3;
     if (row_stride < (size_t)P.xres * 3) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
     return render_device(s, P, d_out, row_stride, false, cuda_stream);
@@ -497,7 +506,7 @@ int rr_render_f32_device(rr_scene *s, const rr_frame_params *params, void *d_out
     if (!s || !d_out) return fail(RR_ERR_BAD_ARG, "scene/d_out is null");
     int rc = check_params(params);
     if (rc) return rc;
-    rr::FrameParams P = to_dev(params);
+    rr::FrameParams P = to_dev(params, s);
     return render_device(s, P, d_out, 0, true, cuda_stream);
 }
 
@@ -548,7 +557,7 @@ int rr_render_rgb8(rr_scene *s, const rr_frame_params *params, uint8_t *out, siz
     if (!s || !out) return fail(RR_ERR_BAD_ARG, "scene/out is null");
     int rc = check_params(params);
     if (rc) return rc;
-    rr::FrameParams P = to_dev(params);
+    rr::FrameParams P = to_dev(params, s);
     const size_t packed = (size_t)P.xres * 3;
     if (row_stride == 0) row_stride = packed;
     if (row_stride < packed) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
@@ -567,7 +576,7 @@ int rr_render_rgb8_async(rr_scene *s, const rr_frame_params *params, uint8_t *ou
     *ticket = -1;
     int rc = check_params(params);
     if (rc) return rc;
-    rr::FrameParams P = to_dev(params);
+    rr::FrameParams P = to_dev(params, s);
     const size_t packed = (size_t)P.xres * 3;
     if (row_stride == 0) row_stride = packed;
     if (row_stride < packed) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
@@ -612,7 +621,7 @@ int rr_render_f32(rr_scene *s, const rr_frame_params *params, float *out_rgb) {
     if (!s || !out_rgb) return fail(RR_ERR_BAD_ARG, "scene/out is null");
     int rc = check_params(params);
     if (rc) return rc;
-    rr::FrameParams P = to_dev(params);
+    rr::FrameParams P = to_dev(params, s);
     const size_t bytes = (size_t)P.xres * P.local_rows * 3 * sizeof(float);
     if (bytes == 0) return RR_OK;
     CU(cudaSetDevice(s->device));
@@ -629,7 +638,7 @@ int rr_render_count(rr_scene *s, const rr_frame_params *params, uint8_t *out, si
     if (!s || !counts) return fail(RR_ERR_BAD_ARG, "scene/counts is null");
     int rc = check_params(params);
     if (rc) return rc;
-    rr::FrameParams P = to_dev(params);
+    rr::FrameParams P = to_dev(params, s);
     const size_t packed = (size_t)P.xres * 3;
     if (row_stride == 0) row_stride = packed;
     if (row_stride < packed) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
@@ -658,7 +667,7 @@ int rr_bands_unpack_device(const rr_frame_params *params, const void *d_packed, 
     if (!d_packed || !d_frame) return fail(RR_ERR_BAD_ARG, "null device pointer");
     int rc = check_params(params);
     if (rc) return rc;
-    rr::FrameParams P = to_dev(params);
+    rr::FrameParams P = to_dev(params, nullptr);
     cudaError_t e = rr::launch_bands_unpack(P, d_packed, shard_stride_bytes, d_frame, reinterpret_cast<cudaStream_t>(cuda_stream));
     if (e != cudaSuccess) return fail_cuda(e, "bands_unpack");
     if (!cuda_stream) CU(cudaStreamSynchronize(nullptr));
@@ -670,7 +679,7 @@ int rr_render_rgb8_placed_device(rr_scene *s, const rr_frame_params *params, voi
     if (!s || !d_frame) return fail(RR_ERR_BAD_ARG, "scene/d_frame is null");
     int rc = check_params(params);
     if (rc) return rc;
-    rr::FrameParams P = to_dev(params);
+    rr::FrameParams P = to_dev(params, s);
     P.placed = 1;
     if (row_stride == 0) row_stride = (size_t)P.xres * 3;
     if (row_stride < (size_t)P.xres * 3) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
@@ -684,7 +693,7 @@ int rr_render_rgb8_placed_signal_device(rr_scene *s, const rr_frame_params *para
     if (!s || !d_frame || !d_flags) return fail(RR_ERR_BAD_ARG, "scene/d_frame/d_flags is null");
     int rc = check_params(params);
     if (rc) return rc;
-    rr::FrameParams P = to_dev(params);
+    rr::FrameParams P = to_dev(params, s);
     P.placed = 1;
     if (row_stride == 0) row_stride = (size_t)P.xres * 3;
     if (row_stride < (size_t)P.xres * 3) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");
@@ -729,7 +738,7 @@ int rr_render_rgb8_placed(rr_scene *s, const rr_frame_params *params, uint8_t *h
     int rc = check_params(params);
     if (rc) return rc;
     CU(cudaSetDevice(s->device));
-    rr::FrameParams P = to_dev(params);
+    rr::FrameParams P = to_dev(params, s);
     const size_t packed = (size_t)P.xres * 3;
     if (row_stride == 0) row_stride = packed;
     if (row_stride < packed) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");

@@ -33,6 +33,10 @@ __device__ __forceinline__ SceneView stage_scene(const DevScene &G, float4 *smem
     S.n_floors = G.n_floors;
     S.sph = G.sph; S.sph_oi = G.sph_oi; S.flo_o = G.flo_o; S.flo_n = G.flo_n; S.flo_oi = G.flo_oi;
     S.bvh_a = G.bvh_a; S.bvh_b = G.bvh_b; S.bvh_w = G.bvh_w; S.bsph = G.bsph; S.bsph_oi = G.bsph_oi; S.n_bvh_nodes = G.n_bvh_nodes;
+    // BVH instances: the first float4s of the dynamic shared memory are the per-thread traversal stacks (trace_smem_bytes)
+    S.stk = reinterpret_cast<uint2 *>(smem);
+    S.stk_stride = (int)blockDim.x;
+    if (BVH) smem += (RR_BVH_SMEM_STACK * TRACE_THREADS * sizeof(uint2)) / sizeof(float4);
     if (!stage) return S;
     const int tf = max(G.n_floors - RR_HEAD_FLOORS, 0);
     const int ts = BVH ? 0 : max(G.n_spheres - RR_HEAD_SPHERES, 0);
@@ -71,7 +75,7 @@ __device__ __forceinline__ SceneView stage_scene(const DevScene &G, float4 *smem
     return S;
 }
 
-template <bool COUNT, bool F32OUT, bool STAGE, bool BVH, int TW>
+template <bool COUNT, bool F32OUT, bool STAGE, bool BVH, int TW, bool HEADONLY>
 __global__ void __launch_bounds__(TRACE_THREADS, RR_TRACE_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHead H, const __grid_constant__ FrameParams P,
              void *__restrict__ out, size_t row_stride, Counters *gcnt, int fast_store, float inv_tiles_x, const Signal sig) {
@@ -132,11 +136,13 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
             if constexpr (TW == 128) {
                 // launcher guarantees: RGB8, W % 128 == 0, 16-byte aligned rows (so every lane's uint4 is aligned)
                 const int ly = ly0;
-                const int orow = P.placed ? local_to_image_row(P, ly) : ly;
+                const int irow = local_to_image_row(P, ly);
+                const int orow = P.placed ? irow : ly;
+                const float ez = prim_ez(P, irow);  // one row: the same for the four sub-tiles
                 unsigned *wb = reinterpret_cast<unsigned *>(rr_wbuf[threadIdx.x >> 5]);
 #pragma unroll 1
                 for (int sub = 0; sub < SUB; ++sub) {
-                    const V3 c = trace_pixel<COUNT, BVH>(G, H, S, P, x0 + sub * 32 + lane, local_to_image_row(P, ly), cnt);
+                    const V3 c = trace_pixel<COUNT, BVH, HEADONLY>(G, H, S, P, prim_ey(P, x0 + sub * 32 + lane), ez, cnt);
                     const unsigned rgb = quantize(c.x) | (quantize(c.y) << 8) | (quantize(c.z) << 16);
                     // word w of the 96-byte sub-run holds bytes 4w..4w+3 = pixels pa (and pa+1); lanes 0..23 own one word
                     const int pa = (4 * lane) / 3;
@@ -154,7 +160,7 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
             const int ix = x0 + col, ly = ly0 + row;
             const bool valid = ix < W && ly < rows;
             V3 c = mk(0.0f, 0.0f, 0.0f);
-            if (valid) c = trace_pixel<COUNT, BVH>(G, H, S, P, ix, local_to_image_row(P, ly), cnt);
+            if (valid) c = trace_pixel<COUNT, BVH, HEADONLY>(G, H, S, P, ix, local_to_image_row(P, ly), cnt);
             if (F32OUT) {
                 if (valid) {
                     float *o = reinterpret_cast<float *>(out) + ((size_t)(P.placed ? local_to_image_row(P, ly) : ly) * W + ix) * 3;
@@ -172,6 +178,7 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
     finish_launch(sig);
 }
 
+static size_t trace_stack_bytes(bool bvh) { return bvh ? (size_t)RR_BVH_SMEM_STACK * TRACE_THREADS * sizeof(uint2) : 0; }
 static size_t trace_smem_bytes(const DevScene &G, bool bvh) {
     const size_t tf = G.n_floors > RR_HEAD_FLOORS ? G.n_floors - RR_HEAD_FLOORS : 0;
     size_t b = tf * (2 * sizeof(float4) + sizeof(int)) + 16;
@@ -181,10 +188,10 @@ static size_t trace_smem_bytes(const DevScene &G, bool bvh) {
     return b + ts * (sizeof(float4) + sizeof(int));
 }
 
-template <bool COUNT, bool F32OUT, bool STAGE, bool BVH, int TW>
-static cudaError_t launch_tw(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
+template <bool COUNT, bool F32OUT, bool STAGE, bool BVH, int TW, bool HEADONLY>
+static cudaError_t launch_hd(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
                              Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, size_t smem, const Signal &sig) {
-    auto kern = trace_kernel<COUNT, F32OUT, STAGE, BVH, TW>;
+    auto kern = trace_kernel<COUNT, F32OUT, STAGE, BVH, TW, HEADONLY>;
     constexpr int TH = TW == 128 ? 1 : 32 / TW;
     cudaError_t e;
     if (smem > 48 * 1024) {
@@ -205,6 +212,18 @@ static cudaError_t launch_tw(const DevScene &G, const SceneHead &H, const FrameP
     const float inv_tx = tiles < (1 << 24) ? 1.0f / (float)tiles_x : 0.0f;
     kern<<<(unsigned)grid, TRACE_THREADS, smem, stream>>>(G, H, P, d_out, row_stride, d_cnt, fast, inv_tx, sig);
     return cudaGetLastError();
+}
+
+// Head-only instance: the whole scene sits in the constant-bank SceneHead (the built-in scene: 1 floor + 4 spheres), the
+// scan has no count checks and no tail loops, nothing is staged.
+template <bool COUNT, bool F32OUT, bool STAGE, bool BVH, int TW>
+static cudaError_t launch_tw(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
+                             Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, size_t smem, const Signal &sig) {
+    if constexpr (!BVH && !COUNT && !F32OUT) {
+        if (G.n_floors <= RR_HEAD_FLOORS && G.n_spheres <= RR_HEAD_SPHERES)
+            return launch_hd<COUNT, F32OUT, false, BVH, TW, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, 0, sig);
+    }
+    return launch_hd<COUNT, F32OUT, STAGE, BVH, TW, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem, sig);
 }
 
 // Tile shape (measured, profiles/r1_s2_tile_schedule.md): 128x1 macro tiles (four 32x1 sub-tiles, one 384-byte store)
@@ -233,8 +252,12 @@ static cudaError_t launch_two(const DevScene &G, const SceneHead &H, const Frame
                               Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh, const Signal &sig) {
     const bool bvh = allow_bvh && G.n_bvh_nodes > 0;
     size_t smem = trace_smem_bytes(G, bvh);
-    const bool stage = smem <= li.smem_optin / 2;  // keep >= 2 blocks per SM resident
+#ifndef RR_BVH_STAGE
+#define RR_BVH_STAGE 1
+#endif
+    const bool stage = (RR_BVH_STAGE || !bvh) && smem + trace_stack_bytes(bvh) <= li.smem_optin / 2;  // keep >= 2 blocks per SM resident
     if (!stage) smem = 0;
+    smem += trace_stack_bytes(bvh);  // the traversal stacks are always there
     if (bvh) return stage ? launch_one<COUNT, F32OUT, true, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem, sig)
                           : launch_one<COUNT, F32OUT, false, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem, sig);
     return stage ? launch_one<COUNT, F32OUT, true, false>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem, sig)

@@ -30,6 +30,10 @@ struct SceneView {
     const float4 *bvh_a, *bvh_b, *bvh_w, *bsph;
     const int *bsph_oi;
     int n_bvh_nodes;
+    // ordered BVH traversal: the first RR_BVH_SMEM_STACK entries of every thread's stack live in shared memory
+    // (entry e of thread t at stk[e * stk_stride + t]: conflict-free), deeper entries in local memory. nullptr: all local.
+    uint2 *stk;
+    int stk_stride;
 };
 
 struct Hit {
@@ -59,12 +63,7 @@ __device__ __forceinline__ void floor_test(const float4 &o, const float4 &n4, in
 // 4 commute with IEEE rounding): d2 = 4q, d = 2*sqrt(q), t0 = -D - sqrt(q), t1 = t0 + 2*sqrt(q), and
 // `d2 >= EPSILON` <=> `q >= EPSILON/4`. Same bits, fewer multiplies.
 template <typename OiFn>
-__device__ __forceinline__ void sphere_test(const float4 &c4, OiFn get_oi, const V3 &vi, const V3 &eye, int ig, bool near_ok,
-                                            bool far_ok, float &t, int &idx) {
-    const V3 wpt = vi - mk(c4.x, c4.y, c4.z);
-    const float D = dot(eye, wpt);
-    const float c = dot(wpt, wpt) - c4.w;
-    const float q = D * D - c;
+__device__ __forceinline__ void sphere_finish(float D, float q, OiFn get_oi, int ig, bool near_ok, bool far_ok, float &t, int &idx) {
     if (q >= F32_EPS_QUARTER) {
         const float sq = sqrtf(q);
         const float t0 = -D - sq;
@@ -84,6 +83,45 @@ __device__ __forceinline__ void sphere_test(const float4 &c4, OiFn get_oi, const
             }
         }
     }
+}
+template <typename OiFn>
+__device__ __forceinline__ void sphere_test(const float4 &c4, OiFn get_oi, const V3 &vi, const V3 &eye, int ig, bool near_ok,
+                                            bool far_ok, float &t, int &idx) {
+    const V3 wpt = vi - mk(c4.x, c4.y, c4.z);
+    const float D = dot(eye, wpt);
+    const float c = dot(wpt, wpt) - c4.w;
+    const float q = D * D - c;
+    sphere_finish(D, q, get_oi, ig, near_ok, far_ok, t, idx);
+}
+
+// Two spheres per instruction (packed f32x2, rr_device.cuh F2): the same operations in the same order as sphere_test(),
+// on the pair arrangement of SceneHead / FrameParams. 16 packed operations form (D, q) of both spheres (32 scalar ones).
+#ifndef RR_PACKED_SCAN
+#define RR_PACKED_SCAN 1  // 0: the same scan with scalar FMUL/FADD on constant-bank operands (A/B builds)
+#endif
+#ifndef RR_GROUP_FINISH
+#define RR_GROUP_FINISH 1
+#endif
+struct PairDQ { F2 D, q; };
+__device__ __forceinline__ F2 dot2(const PackK &K, const F2 &ax, const F2 &ay, const F2 &az, const F2 &bx, const F2 &by, const F2 &bz) {
+    return add2(K, add2(K, mul2(K, ax, bx), mul2(K, ay, by)), mul2(K, az, bz));  // (x*x' + y*y') + z*z'
+}
+__device__ __forceinline__ PairDQ sphere_pair_dq(const PackK &K, const float2 &cx, const float2 &cy, const float2 &cz, const float2 &rr,
+                                                 const V3 &vi, const V3 &eye) {
+    const F2 wx = sub2(K, f2b(vi.x), f2(cx.x, cx.y)), wy = sub2(K, f2b(vi.y), f2(cy.x, cy.y)), wz = sub2(K, f2b(vi.z), f2(cz.x, cz.y));
+    PairDQ r;
+    r.D = dot2(K, f2b(eye.x), f2b(eye.y), f2b(eye.z), wx, wy, wz);
+    const F2 c = sub2(K, dot2(K, wx, wy, wz, wx, wy, wz), f2(rr.x, rr.y));
+    r.q = sub2(K, mul2(K, r.D, r.D), c);
+    return r;
+}
+// primary rays: wpt and c come from the frame constants (FrameParams::pw_*), 7 packed operations per pair
+__device__ __forceinline__ PairDQ sphere_pair_dq_primary(const PackK &K, const float2 &wx, const float2 &wy, const float2 &wz,
+                                                         const float2 &c, const V3 &eye) {
+    PairDQ r;
+    r.D = dot2(K, f2b(eye.x), f2b(eye.y), f2b(eye.z), f2(wx.x, wx.y), f2(wy.x, wy.y), f2(wz.x, wz.y));
+    r.q = sub2(K, mul2(K, r.D, r.D), f2(c.x, c.y));
+    return r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -214,17 +252,40 @@ __device__ __forceinline__ void bvh_scan_ordered(const DevScene &G, const SceneV
     const float cx_lo = (vi.x + e) * ix, cy_lo = (vi.y + e) * iy, cz_lo = (vi.z + e) * iz;
     const float cx_hi = (vi.x - e) * ix, cy_hi = (vi.y - e) * iy, cz_hi = (vi.z - e) * iz;
     constexpr int DONE = 0x7fffffff;
-    int stk_ref[RR_BVH_STACK];
-    float stk_t[RR_BVH_STACK];
+    // Stack of postponed (farther) children with their entry distances. Its hot part is in shared memory: as two local
+    // arrays it was the largest source of local-memory traffic of the BVH instance (profiles/r1_s2_trace_synthetic1024_4k.md:
+    // 14 M local loads + 14 M local stores per 4K frame, 65 % L1 hit rate, 2.17x the framebuffer bytes in DRAM traffic).
+    constexpr int SD = RR_BVH_SMEM_STACK;
+    int ovf_ref[RR_BVH_STACK - SD];
+    float ovf_t[RR_BVH_STACK - SD];
+#ifdef RR_HOSTSIM
+    uint2 hs_stk[SD];
+    uint2 *const stk = hs_stk;
+    const int sst = 1;
+#else
+    uint2 *const stk = S.stk + threadIdx.x;
+    const int sst = S.stk_stride;
+#endif
     int sp = 0, cur = 0;
+    auto push = [&](int ref, float tm) {
+        if (sp < SD) stk[sp * sst] = make_uint2((unsigned)ref, (unsigned)__float_as_int(tm));
+        else { ovf_ref[sp - SD] = ref; ovf_t[sp - SD] = tm; }
+        sp += 1;
+    };
     // pop the next stacked subtree that can still hold a winner (entered at or before the current best hit)
     auto pop = [&]() {
         float tm;
         do {
             if (sp == 0) { cur = DONE; return; }
             sp -= 1;
-            cur = stk_ref[sp];
-            tm = stk_t[sp];
+            if (sp < SD) {
+                const uint2 e = stk[sp * sst];
+                cur = (int)e.x;
+                tm = __int_as_float((int)e.y);
+            } else {
+                cur = ovf_ref[sp - SD];
+                tm = ovf_t[sp - SD];
+            }
         } while (tm > t);  // NaN: visit
     };
     while (cur != DONE) {
@@ -239,9 +300,7 @@ __device__ __forceinline__ void bvh_scan_ordered(const DevScene &G, const SceneV
             const int l = __float_as_int(n3.x), r = __float_as_int(n3.y);
             if (!rej_l && !rej_r) {
                 const bool left_first = L.lo <= R.lo;
-                stk_ref[sp] = left_first ? r : l;
-                stk_t[sp] = left_first ? R.lo : L.lo;
-                sp += 1;
+                push(left_first ? r : l, left_first ? R.lo : L.lo);
                 cur = left_first ? l : r;
             } else if (!rej_l) {
                 cur = l;
@@ -262,18 +321,33 @@ __device__ __forceinline__ void bvh_scan_ordered(const DevScene &G, const SceneV
 }
 
 // scene-level raycast, render.rs:993-1018
-template <bool BVH>
-__device__ __forceinline__ Hit raycast(const DevScene &G, const SceneHead &H, const SceneView &S, const V3 &vi, const V3 &eye,
-                                       int ig, unsigned flags) {
+// HEADONLY: the whole scene is in the SceneHead (<= RR_HEAD_FLOORS floors, <= RR_HEAD_SPHERES spheres; unused slots hold
+// never-hit objects, fill_head_pairs): no count checks, no tail loops. PRIMARY: the ray starts at the camera (ig = -1,
+// flags = 0) and the origin-dependent terms come from the frame constants.
+template <bool BVH, bool HEADONLY, bool PRIMARY>
+__device__ __forceinline__ Hit raycast(const DevScene &G, const SceneHead &H, const SceneView &S, const FrameParams &P, const V3 &vi,
+                                       const V3 &eye, int ig, unsigned flags) {
     float t = RR_INF;
     int idx = 0;
 #pragma unroll
-    for (int f = 0; f < RR_HEAD_FLOORS; ++f)
-        if (f < S.n_floors) floor_test(H.flo_o[f], H.flo_n[f], H.flo_oi[f], vi, eye, ig, t, idx);
-    for (int f = RR_HEAD_FLOORS; f < S.n_floors; ++f)
-        floor_test(S.flo_o[f], S.flo_n[f], S.flo_oi[f], vi, eye, ig, t, idx);
-    const bool near_ok = (flags & OUTONLY) == 0;
-    const bool far_ok = (flags & INONLY) == 0;
+    for (int f = 0; f < RR_HEAD_FLOORS; ++f) {
+        if (HEADONLY || f < S.n_floors) {
+            if (PRIMARY && !BVH) {
+                // floor_test() with -(n.wpt) taken from the frame constants
+                const float w = dot(mk(H.flo_n[f].x, H.flo_n[f].y, H.flo_n[f].z), eye);
+                if (w <= 0.0f) {
+                    const float t0 = P.pf_nd[f] / w;
+                    if (t0 >= 0.0f && t0 < t) { t = t0; idx = H.flo_oi[f]; }
+                }
+            } else {
+                floor_test(H.flo_o[f], H.flo_n[f], H.flo_oi[f], vi, eye, ig, t, idx);
+            }
+        }
+    }
+    if (!HEADONLY)
+        for (int f = RR_HEAD_FLOORS; f < S.n_floors; ++f) floor_test(S.flo_o[f], S.flo_n[f], S.flo_oi[f], vi, eye, ig, t, idx);
+    const bool near_ok = PRIMARY ? true : (flags & OUTONLY) == 0;
+    const bool far_ok = PRIMARY ? true : (flags & INONLY) == 0;
     if constexpr (BVH) {
         // The cull is geometric; the reference's test is geometric only for unit directions (it drops the
         // |eye|^2 factor of the quadratic). Directions are unit to a few ulp everywhere except after a bounce
@@ -292,77 +366,112 @@ __device__ __forceinline__ Hit raycast(const DevScene &G, const SceneHead &H, co
                 sphere_test(S.bsph[s], [&] { return S.bsph_oi[s]; }, vi, eye, ig, near_ok, far_ok, t, idx);
         }
     } else {
+        // (D, q) of every head sphere first (slots beyond the scene's spheres hold never-hit padding, so there are no count
+        // checks in either instance), then ONE branch: most rays of most warps (sky, floor) miss every sphere, and the
+        // candidate logic of all of them is skipped together when no lane has q >= EPSILON/4 for any sphere (a NaN q is
+        // ignored by fmaxf and fails the per-sphere test anyway).
+        float Ds[2 * RR_HEAD_PAIRS], qs[2 * RR_HEAD_PAIRS];
+#if RR_PACKED_SCAN
+        const PackK K{f2(P.pk_one.x, P.pk_one.y), f2(P.pk_nz.x, P.pk_nz.y), f2(P.pk_neg1.x, P.pk_neg1.y)};
 #pragma unroll
-        for (int s = 0; s < RR_HEAD_SPHERES; ++s)
-            if (s < S.n_spheres) sphere_test(H.sph[s], [&] { return H.sph_oi[s]; }, vi, eye, ig, near_ok, far_ok, t, idx);
+        for (int p = 0; p < RR_HEAD_PAIRS; ++p) {
+            const PairDQ dq = PRIMARY ? sphere_pair_dq_primary(K, P.pw_x[p], P.pw_y[p], P.pw_z[p], P.pw_c[p], eye)
+                                      : sphere_pair_dq(K, H.pcx[p], H.pcy[p], H.pcz[p], H.prr[p], vi, eye);
+            Ds[2 * p] = f2lo(dq.D); qs[2 * p] = f2lo(dq.q);
+            Ds[2 * p + 1] = f2hi(dq.D); qs[2 * p + 1] = f2hi(dq.q);
+        }
+#else
+#pragma unroll
+        for (int s = 0; s < 2 * RR_HEAD_PAIRS; ++s) {
+            const int p = s >> 1, k = s & 1;  // compile-time after unrolling: the constants are c[][] operands of the FMUL/FADDs
+            if (PRIMARY) {
+                const V3 wpt = mk(k ? P.pw_x[p].y : P.pw_x[p].x, k ? P.pw_y[p].y : P.pw_y[p].x, k ? P.pw_z[p].y : P.pw_z[p].x);
+                Ds[s] = dot(eye, wpt);
+                qs[s] = Ds[s] * Ds[s] - (k ? P.pw_c[p].y : P.pw_c[p].x);
+            } else {
+                const V3 wpt = vi - mk(k ? H.pcx[p].y : H.pcx[p].x, k ? H.pcy[p].y : H.pcy[p].x, k ? H.pcz[p].y : H.pcz[p].x);
+                Ds[s] = dot(eye, wpt);
+                const float c = dot(wpt, wpt) - (k ? H.prr[p].y : H.prr[p].x);
+                qs[s] = Ds[s] * Ds[s] - c;
+            }
+        }
+#endif
+        float qmax = qs[0];
+#pragma unroll
+        for (int s = 1; s < 2 * RR_HEAD_PAIRS; ++s) qmax = fmaxf(qmax, qs[s]);
+        if (!RR_GROUP_FINISH || qmax >= F32_EPS_QUARTER) {
+#pragma unroll
+            for (int s = 0; s < RR_HEAD_SPHERES; ++s)  // (the padded high half of an odd head can never hit; its index is not stored)
+                sphere_finish(Ds[s], qs[s], [&] { return H.sph_oi[s]; }, ig, near_ok, far_ok, t, idx);
+        }
+        if (!HEADONLY) {
 #pragma unroll 4
-        for (int s = RR_HEAD_SPHERES; s < S.n_spheres; ++s)
-            sphere_test(S.sph[s], [&] { return S.sph_oi[s]; }, vi, eye, ig, near_ok, far_ok, t, idx);
+            for (int s = RR_HEAD_SPHERES; s < S.n_spheres; ++s)
+                sphere_test(S.sph[s], [&] { return S.sph_oi[s]; }, vi, eye, ig, near_ok, far_ok, t, idx);
+        }
     }
     return Hit{t, idx};
 }
 
-struct TraceFrame {  // a suspended raytrace() frame waiting for its refraction child
+// A suspended raytrace() frame waiting for its refraction child: 68 bytes, the last 24 (continuation ray) written and
+// read only when the parent's bounce loop goes on after this hit.
+struct TraceFrame {
     float ret[3];
     float fcs[3];   // fcs before this hit was accumulated
     float A[3];     // (kd*k1 + k2) * (1 - f)
     float f;
+    unsigned meta;  // object that was hit (== ig of the continuation) | lev << 22 | continuation flags << 28 | cont << 31
     float vi[3];    // continuation ray (valid when cont)
     float eye[3];
-    int ig;         // object that was hit (== ig of the continuation)
-    int lev;
-    unsigned flags; // continuation flags
-    int cont;       // will the parent's bounce loop continue after this hit?
 };
+// ig < 2^22 (rr_scene_create rejects larger scenes for the trace stack), lev <= 32 (6 bits), flags in {0, OUTONLY, INONLY}
+__device__ __forceinline__ unsigned pack_meta(int ig, int lev, bool cont, unsigned flags) {
+    return (unsigned)ig | ((unsigned)lev << 22) | (flags << 28) | (cont ? 0x80000000u : 0u);
+}
+__device__ __forceinline__ int meta_ig(unsigned m) { return (int)(m & 0x3fffffu); }
+__device__ __forceinline__ int meta_lev(unsigned m) { return (int)((m >> 22) & 0x3fu); }
+__device__ __forceinline__ unsigned meta_flags(unsigned m) { return (m >> 28) & 3u; }
+__device__ __forceinline__ bool meta_cont(unsigned m) { return (m & 0x80000000u) != 0u; }
 
 constexpr int RR_MAX_STACK = 32;  // >= max_refractions (checked on the host)
 
-template <bool COUNT, bool BVH>
+// One pixel. The loop is rotated: its body is "consume the hit of the last scan, set up the next ray, scan", and the
+// first scan (the primary ray, whose origin-dependent terms are frame constants) is peeled off in front of it. There is
+// still ONE general scan site, shared by trace rays and shadow rays of lanes in different phases.
+template <bool COUNT, bool BVH, bool HEADONLY = false>
 __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneHead &H, const SceneView &S, const FrameParams &P,
-                                          int ix, int iy, Counters &cnt) {
+                                          float ey, float ez, Counters &cnt) {
     const V3 light = mk(P.light[0], P.light[1], P.light[2]);
     // current trace ray of the running raytrace() frame
     V3 vi = mk(P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]);
-    V3 eye = primary_ray(P, ix, iy);
-    int lev = 0, ig = -1, depth = 0;
+    V3 eye = primary_dir(P, ey, ez);
+    int lev = 1 /* render.rs:1157, first iteration */, ig = -1, depth = 0;
     unsigned flags = 0;
     V3 ret = mk(0.0f, 0.0f, 0.0f), fcs = mk(1.0f, 1.0f, 1.0f);
     TraceFrame stack[RR_MAX_STACK];
     int ray_class = 0;  // 0 primary, 1 refract child's first ray, 2 reflect continuation
     // shading() state carried across the shadow ray
-    bool shadow_phase = false;
+    bool shadow_phase = false;  // which kind of ray produced `h`
     int hidx = 0;
     V3 pt = vi, n = vi;
     float diffuse_intensity = 0.0f, reflection_intensity = 0.0f;
-    if (COUNT) cnt.pixels++;
+    if (COUNT) {
+        cnt.pixels++;
+        cnt.primary++;
+        cnt.object_tests += (unsigned long long)G.n_objects;
+        cnt.sphere_tests += (unsigned long long)spheres_tested(G, -1);
+    }
+    // BVH instances do not peel the primary scan: a second copy of the traversal costs more in instruction-cache misses
+    // than the peeled scan saves (measured: 2.05 -> 2.17 ms on the 1 024-sphere scene); they enter the loop at the scan.
+    Hit h{RR_INF, 0};
+    bool enter_at_scan = BVH;
+    if (!BVH) h = raycast<BVH, HEADONLY, true>(G, H, S, P, vi, eye, -1, 0u);
 
     for (;;) {
-        // ---- the one scene scan: either the frame's trace ray or the shadow ray of a hit ----
-        V3 ro, rd;
-        int rig;
-        unsigned rfl;
-        if (!shadow_phase) {
-            lev += 1;  // render.rs:1157
-            ro = vi; rd = eye; rig = ig; rfl = flags;
-            if (COUNT) {
-                if (ray_class == 0) cnt.primary++;
-                else if (ray_class == 1) cnt.refract++;
-                else cnt.reflect++;
-            }
-        } else {
-            ro = pt + (light * F32_EPSILON);  // render.rs:1034
-            rd = light; rig = hidx; rfl = 0u;
-            if (COUNT) {
-                cnt.shadow++;
-                if (__ldg(&G.obj_b[hidx]).x == 0) cnt.sphere_hits++;
-            }
-        }
-        if (COUNT) {
-            cnt.object_tests += (unsigned long long)(G.n_objects - (rig >= 0 ? 1 : 0));
-            cnt.sphere_tests += (unsigned long long)spheres_tested(G, rig);
-        }
-        const Hit h = raycast<BVH>(G, H, S, ro, rd, rig, rfl);
-
+        V3 ro = vi, rd = eye;
+        int rig = -1;
+        unsigned rfl = 0u;
+        if (!enter_at_scan) {
         bool frame_done = false;
         if (!shadow_phase) {
             if (h.t < RR_INF) {
@@ -388,12 +497,12 @@ __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneHead &H,
                     if (ri > 0.0f) reflection_intensity = rs_powi(ri, pn);
                 }
                 shadow_phase = true;
-                continue;
+            } else {
+                if (COUNT) cnt.bg_evals++;
+                const V3 bg = bgcolor(P, eye);  // render.rs:1213-1216
+                ret = mk(ret.x + bg.x * fcs.x, ret.y + bg.y * fcs.y, ret.z + bg.z * fcs.z);
+                frame_done = true;
             }
-            if (COUNT) cnt.bg_evals++;
-            const V3 bg = bgcolor(P, eye);  // render.rs:1213-1216
-            ret = mk(ret.x + bg.x * fcs.x, ret.y + bg.y * fcs.y, ret.z + bg.z * fcs.z);
-            frame_done = true;
         } else {
             // ---- second half of shading(), render.rs:1048-1139 ----
             shadow_phase = false;
@@ -426,18 +535,16 @@ __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneHead &H,
                 F.fcs[0] = fcs.x; F.fcs[1] = fcs.y; F.fcs[2] = fcs.z;
                 F.A[0] = face.x * omf; F.A[1] = face.y * omf; F.A[2] = face.z * omf;
                 F.f = f;
-                F.ig = idx;
-                F.lev = lev;
                 // what the parent does after `ret += face*fcs; fcs *= ks` (render.rs:1175-1211)
                 const V3 nf = mk(fcs.x * ks.x, fcs.y * ks.y, fcs.z * ks.z);
                 const bool cont = !(idx == 0) && !((nf.x + nf.y + nf.z) <= 0.1f) && !(lev >= P.max_reflections);
-                F.cont = cont ? 1 : 0;
+                F.meta = pack_meta(idx, lev, cont, 0u);
                 if (cont) {
                     const float en2 = -2.0f * dot(eye, n);
                     const V3 e2 = eye + n * en2;
                     F.vi[0] = pt.x; F.vi[1] = pt.y; F.vi[2] = pt.z;
                     F.eye[0] = e2.x; F.eye[1] = e2.y; F.eye[2] = e2.z;
-                    F.flags = dot(n, e2) < 0.0f ? OUTONLY : INONLY;
+                    F.meta = pack_meta(idx, lev, true, dot(n, e2) < 0.0f ? OUTONLY : INONLY);
                 }
                 depth += 1;
                 vi = pt3;
@@ -447,21 +554,21 @@ __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneHead &H,
                 ret = mk(0.0f, 0.0f, 0.0f);
                 fcs = mk(1.0f, 1.0f, 1.0f);
                 ray_class = 1;
-                continue;  // child starts with lev = nest; the trace phase increments it
-            }
-
-            // ---- back in raytrace(), render.rs:1173-1211 ----
-            ret = mk(ret.x + face.x * fcs.x, ret.y + face.y * fcs.y, ret.z + face.z * fcs.z);
-            fcs = mk(fcs.x * ks.x, fcs.y * ks.y, fcs.z * ks.z);
-            if (idx == 0 || (fcs.x + fcs.y + fcs.z) <= 0.1f || lev >= P.max_reflections) {
-                frame_done = true;
+                // the child starts with lev = nest; the increment below makes it nest + 1
             } else {
-                vi = pt;
-                const float en2 = -2.0f * dot(eye, n);
-                eye = eye + n * en2;
-                flags = dot(n, eye) < 0.0f ? OUTONLY : INONLY;
-                ig = idx;
-                ray_class = 2;
+                // ---- back in raytrace(), render.rs:1173-1211 ----
+                ret = mk(ret.x + face.x * fcs.x, ret.y + face.y * fcs.y, ret.z + face.z * fcs.z);
+                fcs = mk(fcs.x * ks.x, fcs.y * ks.y, fcs.z * ks.z);
+                if (idx == 0 || (fcs.x + fcs.y + fcs.z) <= 0.1f || lev >= P.max_reflections) {
+                    frame_done = true;
+                } else {
+                    vi = pt;
+                    const float en2 = -2.0f * dot(eye, n);
+                    eye = eye + n * en2;
+                    flags = dot(n, eye) < 0.0f ? OUTONLY : INONLY;
+                    ig = idx;
+                    ray_class = 2;
+                }
             }
         }
 
@@ -473,19 +580,50 @@ __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneHead &H,
             const float f = F.f;
             const V3 face = mk(F.A[0] + ret.x * f, F.A[1] + ret.y * f, F.A[2] + ret.z * f);
             ret = mk(F.ret[0] + face.x * F.fcs[0], F.ret[1] + face.y * F.fcs[1], F.ret[2] + face.z * F.fcs[2]);
-            if (F.cont) {
-                const DevMaterial &pm = G.mat[__ldg(&G.obj_b[F.ig]).z];
+            const unsigned meta = F.meta;
+            if (meta_cont(meta)) {
+                ig = meta_ig(meta);
+                const DevMaterial &pm = G.mat[__ldg(&G.obj_b[ig]).z];
                 fcs = mk(F.fcs[0] * pm.specular[0], F.fcs[1] * pm.specular[1], F.fcs[2] * pm.specular[2]);
                 vi = mk(F.vi[0], F.vi[1], F.vi[2]);
                 eye = mk(F.eye[0], F.eye[1], F.eye[2]);
-                flags = F.flags;
-                ig = F.ig;
-                lev = F.lev;
+                flags = meta_flags(meta);
+                lev = meta_lev(meta);
                 ray_class = 2;
                 frame_done = false;
             }
         }
+
+        // ---- the one general scene scan: the frame's next trace ray or the shadow ray of the hit ----
+        if (!shadow_phase) {
+            lev += 1;  // render.rs:1157
+            ro = vi; rd = eye; rig = ig; rfl = flags;
+            if (COUNT) {
+                if (ray_class == 1) cnt.refract++;
+                else cnt.reflect++;
+            }
+        } else {
+            ro = pt + (light * F32_EPSILON);  // render.rs:1034
+            rd = light; rig = hidx; rfl = 0u;
+            if (COUNT) {
+                cnt.shadow++;
+                if (__ldg(&G.obj_b[hidx]).x == 0) cnt.sphere_hits++;
+            }
+        }
+        if (COUNT) {
+            cnt.object_tests += (unsigned long long)(G.n_objects - (rig >= 0 ? 1 : 0));
+            cnt.sphere_tests += (unsigned long long)spheres_tested(G, rig);
+        }
+        }  // !enter_at_scan
+        enter_at_scan = false;
+        h = raycast<BVH, HEADONLY, false>(G, H, S, P, ro, rd, rig, rfl);
     }
+}
+
+template <bool COUNT, bool BVH, bool HEADONLY = false>
+__device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneHead &H, const SceneView &S, const FrameParams &P,
+                                          int ix, int iy, Counters &cnt) {
+    return trace_pixel<COUNT, BVH, HEADONLY>(G, H, S, P, prim_ey(P, ix), prim_ez(P, iy), cnt);
 }
 
 }  // namespace rr

@@ -115,6 +115,7 @@ _P = C.c_void_p
 PROTOTYPES = {
     "rr_abi_version": (C.c_int, []),
     "rr_last_error": (C.c_char_p, []),
+    "rr_build_info": (C.c_char_p, []),
     "rr_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "rr_scene_create": (C.c_int, [C.POINTER(rr_scene_desc), C.c_int, C.POINTER(_P)]),
     "rr_scene_destroy": (C.c_int, [_P]),
@@ -162,6 +163,19 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    if LIB_PATH == os.path.join(_HERE, "libray_rust_b200.so"):
+        # The in-tree binary must be the checked-in source: built files are not in git history but do travel to the
+        # GPU box, so a stale one could otherwise be loaded silently. Compare the hash compiled into it with the
+        # sources next to it and rebuild when they differ (nvcc, a few minutes, once).
+        import importlib.util
+        import sys
+
+        spec = importlib.util.spec_from_file_location("rr_build", os.path.join(_HERE, "build.py"))
+        b = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(b)
+        if not b.is_current(LIB_PATH):
+            sys.stderr.write("ray_rust_b200: libray_rust_b200.so is missing or does not match csrc/ (content hash); rebuilding\n")
+            b.build()
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} not found: the CUDA library is not built. Run `python -c 'import __graft_entry__ as g; "

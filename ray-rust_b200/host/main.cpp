@@ -29,7 +29,7 @@ static void usage() {
 int main(int argc, char **argv) {
     std::vector<std::string> pos;
     std::string threads = "8", output = "foo.png", glow, ser, deser, port = "3000", gpu = "0";
-    bool raymarch = false, webserver = false, have_glow = false, have_ser = false, have_deser = false;
+    bool raymarch = false, webserver = false, have_glow = false, have_ser = false, have_deser = false, have_gpu = false;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto val = [&](std::string &dst) {
@@ -44,7 +44,7 @@ int main(int argc, char **argv) {
         else if (a == "-d" || a == "--deserialize_file") { val(deser); have_deser = true; }
         else if (a == "-w" || a == "--webserver") webserver = true;
         else if (a == "-p" || a == "--port_no") val(port);
-        else if (a == "--gpu") val(gpu);
+        else if (a == "--gpu") { val(gpu); have_gpu = true; }
         else if (a == "-h" || a == "--help") { usage(); return 0; }
         else pos.push_back(a);
     }
@@ -89,11 +89,12 @@ int main(int argc, char **argv) {
         const int device = atoi(gpu.c_str());
         auto start = std::chrono::steady_clock::now();  // main.rs:316: the timed region includes the PNG encode
         if (!ren.camera_motion.empty()) {
-            rr::render_frames(ren, (size_t)width, (size_t)height, [&](int i, const std::vector<uint8_t> &data) {
-                try { rr::save_png_rgb8(output + std::to_string(i) + ".png", data.data(), (uint32_t)width, (uint32_t)height); } catch (...) {}
-            }, thread_count, device);
+            // frames are dealt to every visible GPU unless --gpu pins one (render.rs:926-989, pipelined)
+            rr::render_frames(ren, (size_t)width, (size_t)height, [&](int i, const uint8_t *data, size_t) {
+                try { rr::save_png_rgb8(output + std::to_string(i) + ".png", data, (uint32_t)width, (uint32_t)height); } catch (...) {}
+            }, thread_count, have_gpu ? std::vector<int>{device} : std::vector<int>{});
         } else {
-            std::vector<uint8_t> data((size_t)3 * width * height);
+            rr::PinnedFrame data((size_t)3 * width * height);  // page-locked: asynchronous D2H at full PCIe rate
             rr::render_rgb8(ren, data.data(), device);
             rr::save_png_rgb8(output, data.data(), (uint32_t)width, (uint32_t)height);
         }

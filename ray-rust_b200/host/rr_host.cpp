@@ -4,6 +4,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <deque>
+#include <mutex>
 
 namespace rr {
 
@@ -167,29 +169,56 @@ DeviceScene::~DeviceScene() {
     if (handle) rr_scene_destroy(handle);
 }
 
-static rr_scene *device_scene(const RenderEnv &ren, int device) {
-    if (!ren.device_) ren.device_ = std::make_shared<DeviceScene>(ren, device);
-    return ren.device_->handle;
+// One flattened copy of the scene per GPU, built at the first render on that GPU. The cache sits in a const RenderEnv
+// (render() takes `&RenderEnv`, and several threads may render one environment, webserver.rs:268-280), so it is locked.
+static std::mutex g_device_cache_mu;
+static std::shared_ptr<DeviceScene> device_scene(const RenderEnv &ren, int device) {
+    std::lock_guard<std::mutex> lk(g_device_cache_mu);
+    auto it = ren.device_.find(device);
+    if (it != ren.device_.end()) return it->second;
+    auto d = std::make_shared<DeviceScene>(ren, device);
+    ren.device_[device] = d;
+    return d;
+}
+void RenderEnv::invalidate() {
+    std::lock_guard<std::mutex> lk(g_device_cache_mu);
+    device_.clear();
+}
+
+PinnedFrame::~PinnedFrame() {
+    if (p_) rr_host_free(p_);
+}
+void PinnedFrame::resize(size_t bytes) {
+    if (bytes <= n_) return;
+    if (p_) rr_host_free(p_);
+    p_ = nullptr;
+    n_ = 0;
+    void *q = nullptr;
+    check(rr_host_alloc(bytes, &q));
+    p_ = static_cast<uint8_t *>(q);
+    n_ = bytes;
 }
 
 void render(const RenderEnv &ren, const PointProc &pointproc, int /*thread_count*/, int device) {
-    rr_scene *h = device_scene(ren, device);
+    auto scene = device_scene(ren, device);
     rr_frame_params p = ren.frame_params();
-    std::vector<float> buf((size_t)3 * ren.xres * ren.yres);
-    if (buf.empty()) return;
-    check(rr_render_f32(h, &p, buf.data()));
+    const size_t n = (size_t)3 * ren.xres * ren.yres;
+    if (n == 0) return;
+    PinnedFrame buf(n * sizeof(float));
+    const float *px = reinterpret_cast<const float *>(buf.data());
+    check(rr_render_f32(scene->handle, &p, reinterpret_cast<float *>(buf.data())));
     for (int iy = 0; iy < ren.yres; ++iy)
         for (int ix = 0; ix < ren.xres; ++ix) {
-            const float *c = &buf[(size_t)3 * ((size_t)iy * ren.xres + ix)];
+            const float *c = &px[(size_t)3 * ((size_t)iy * ren.xres + ix)];
             pointproc(ix, iy, RenderColor(c[0], c[1], c[2]));
         }
 }
 
 void render_rgb8(const RenderEnv &ren, uint8_t *data, int device) {
-    rr_scene *h = device_scene(ren, device);
+    auto scene = device_scene(ren, device);
     rr_frame_params p = ren.frame_params();
     if (ren.xres == 0 || ren.yres == 0) return;
-    check(rr_render_rgb8(h, &p, data, 0));
+    check(rr_render_rgb8(scene->handle, &p, data, 0));
 }
 
 // hermite_interpolate, render.rs:907-924
@@ -206,9 +235,9 @@ static Vec3 hermite(float t, const Vec3 &x0, const Vec3 &x1, const Vec3 &v0, con
     return Vec3(hermite_f32(t, x0.x, x1.x, v0.x, v1.x), hermite_f32(t, x0.y, x1.y, v0.y, v1.y), hermite_f32(t, x0.z, x1.z, v0.z, v1.z));
 }
 
-void render_frames(RenderEnv &ren, size_t width, size_t height,
-                   const std::function<void(int, const std::vector<uint8_t> &)> &frame_proc, int thread_count, int device) {
-    (void)thread_count;
+// The camera of every frame render_frames() produces, render.rs:935-971 (Hermite position, slerp or look-at rotation).
+std::vector<Camera> interpolate_camera_motion(const RenderEnv &ren, bool verbose) {
+    std::vector<Camera> out;
     Camera prev_camera = ren.camera;
     Vec3 prev_velocity = Vec3::zero();
     float total_frames = 0.0f;
@@ -218,29 +247,82 @@ void render_frames(RenderEnv &ren, size_t width, size_t height,
     for (size_t n = 0; n < ren.camera_motion.size(); ++n) {
         const CameraKeyframe &frame = ren.camera_motion[n];
         const Vec3 v0 = prev_velocity, v1 = frame.velocity;
-        printf("keyframe %zu / %zu, v0: %g,%g,%g\n", n, ren.camera_motion.size(), v0.x, v0.y, v0.z);
+        if (verbose) printf("keyframe %zu / %zu, v0: %g,%g,%g\n", n, ren.camera_motion.size(), v0.x, v0.y, v0.z);
         const int count = (int)(frame.duration / frame_step);
         for (int i = 0; i < count; ++i) {
             const float f = (float)i / (frame.duration / frame_step);
-            printf("Rendering frame %d / %g, v0: %g,%g\n", accum_frame, total_frames, v0.x, v0.y);
-            ren.camera.position = hermite(f, prev_camera.position, frame.camera.position, v0, v1);
+            if (verbose) printf("Rendering frame %d / %g, v0: %g,%g\n", accum_frame, total_frames, v0.x, v0.y);
+            Camera cam = ren.camera;
+            cam.position = hermite(f, prev_camera.position, frame.camera.position, v0, v1);
             if (frame.has_target) {  // look-at, render.rs:961-967
-                Vec3 delta = frame.camera_target - ren.camera.position;
+                Vec3 delta = frame.camera_target - cam.position;
                 float pitch = atan2f(delta.y, std::sqrt(delta.x * delta.x + delta.z * delta.z));
                 float yaw = -atan2f(delta.z, delta.x);
-                ren.camera.rotation = Quat::rotation(yaw, 0.0f, 1.0f, 0.0f) * Quat::rotation(pitch, 0.0f, 0.0f, 1.0f) *
-                                      Quat::rotation(-PI / 2.0f, 1.0f, 0.0f, 0.0f);
+                cam.rotation = Quat::rotation(yaw, 0.0f, 1.0f, 0.0f) * Quat::rotation(pitch, 0.0f, 0.0f, 1.0f) *
+                               Quat::rotation(-PI / 2.0f, 1.0f, 0.0f, 0.0f);
             } else {
-                ren.camera.rotation = prev_camera.rotation.slerp(frame.camera.rotation, f);
+                cam.rotation = prev_camera.rotation.slerp(frame.camera.rotation, f);
             }
-            std::vector<uint8_t> data(3 * width * height);
-            render_rgb8(ren, data.data(), device);  // the scene handle stays resident; only the camera changes
-            frame_proc(accum_frame, data);
+            out.push_back(cam);
             accum_frame += 1;
         }
         prev_camera = frame.camera;
         prev_velocity = frame.velocity;
     }
+    return out;
+}
+
+void render_frames(RenderEnv &ren, size_t width, size_t height, const FrameProc &frame_proc, int thread_count,
+                   const std::vector<int> &devices_in) {
+    (void)thread_count;
+    if ((long long)width != ren.xres || (long long)height != ren.yres)
+        throw RenderError(RR_ERR_BAD_ARG, "render_frames: width/height differ from the environment's resolution");
+    const std::vector<Camera> cams = interpolate_camera_motion(ren, true);
+    if (cams.empty()) return;
+    std::vector<int> devices = devices_in;
+    if (devices.empty()) {
+        int n = 0;
+        check(rr_device_count(&n));
+        for (int d = 0; d < n; ++d) devices.push_back(d);
+        if (devices.empty()) throw RenderError(RR_ERR_CUDA, "no CUDA device");
+    }
+    if (devices.size() > cams.size()) devices.resize(cams.size());
+    const size_t bytes = 3 * width * height;
+    constexpr int DEPTH = 2;  // frames in flight per GPU (each has 4 lanes; two keep kernel, copy and frame_proc overlapped)
+    struct Slot { std::shared_ptr<DeviceScene> scene; PinnedFrame buf; int32_t ticket = -1; };
+    std::vector<Slot> slots(devices.size() * DEPTH);
+    for (size_t k = 0; k < slots.size(); ++k) {
+        slots[k].scene = device_scene(ren, devices[k % devices.size()]);
+        slots[k].buf.resize(bytes ? bytes : 1);
+    }
+    rr_frame_params base = ren.frame_params();
+    auto submit = [&](size_t i) {
+        Slot &s = slots[i % slots.size()];
+        rr_frame_params p = base;
+        const Camera &c = cams[i];
+        p.cam_position[0] = c.position.x; p.cam_position[1] = c.position.y; p.cam_position[2] = c.position.z;
+        p.cam_rotation[0] = c.rotation.x; p.cam_rotation[1] = c.rotation.y; p.cam_rotation[2] = c.rotation.z; p.cam_rotation[3] = c.rotation.w;
+        check(rr_render_rgb8_async(s.scene->handle, &p, s.buf.data(), 0, &s.ticket));
+    };
+    auto drain = [&]() {  // never leave tickets behind, whatever happens
+        for (Slot &s : slots)
+            if (s.ticket >= 0) { rr_render_wait(s.scene->handle, s.ticket, nullptr); s.ticket = -1; }
+    };
+    try {
+        for (size_t i = 0; i < cams.size() && i < slots.size(); ++i) submit(i);
+        for (size_t i = 0; i < cams.size(); ++i) {
+            Slot &s = slots[i % slots.size()];
+            const int32_t t = s.ticket;
+            s.ticket = -1;
+            check(rr_render_wait(s.scene->handle, t, nullptr));
+            frame_proc((int)i, s.buf.data(), bytes);       // the next frames are rendering meanwhile
+            if (i + slots.size() < cams.size()) submit(i + slots.size());
+        }
+    } catch (...) {
+        drain();
+        throw;
+    }
+    ren.camera = cams.back();  // the reference leaves the last interpolated pose in ren.camera
 }
 
 // ---- built-in scene, main.rs:154-276 --------------------------------------------------------------

@@ -152,7 +152,9 @@ public:
     std::string serialize() const;            // render.rs:735-760
     void deserialize(const std::string &s);   // render.rs:762-799; throws DeserializeError
     rr_frame_params frame_params() const;
-    void invalidate() { device_.reset(); }
+    // Drops the device-resident copies of the scene. materials()/objects() call it; call it yourself after editing a
+    // shared RenderMaterial in place through a MaterialRef (the device copy is a snapshot taken at the first render).
+    void invalidate();
 
     Camera camera;
     std::vector<CameraKeyframe> camera_motion;
@@ -166,7 +168,7 @@ public:
     bool glow_some_ = false;
     float glow_value_ = 0.0f;
     int max_reflections = MAX_REFLECTIONS, max_refractions = MAX_REFRACTIONS;
-    mutable std::shared_ptr<DeviceScene> device_;  // flattened scene resident on the GPU (built lazily)
+    mutable std::map<int, std::shared_ptr<DeviceScene>> device_;  // flattened scene resident on GPU <key> (built lazily, locked)
 };
 
 // flattened POD view of a RenderEnv for rr_scene_create (pointers are into this object)
@@ -186,15 +188,41 @@ public:
     rr_scene *handle = nullptr;
 };
 
+// Page-locked host frame (rr_host_alloc): what every caller of this layer hands to the C ABI, so that device-to-host
+// copies run asynchronously at full PCIe rate and long kernels can store straight into the frame.
+class PinnedFrame {
+public:
+    PinnedFrame() = default;
+    explicit PinnedFrame(size_t bytes) { resize(bytes); }
+    PinnedFrame(const PinnedFrame &) = delete;
+    PinnedFrame &operator=(const PinnedFrame &) = delete;
+    PinnedFrame(PinnedFrame &&o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+    ~PinnedFrame();
+    void resize(size_t bytes);  // grows only; throws RenderError when no CUDA device is usable
+    uint8_t *data() const { return p_; }
+    size_t size() const { return n_; }
+private:
+    uint8_t *p_ = nullptr;
+    size_t n_ = 0;
+};
+
 using PointProc = std::function<void(int, int, const RenderColor &)>;
 // render(), render.rs:801-805. Calls pointproc(x, y, colour) once per pixel, row-major, on the caller
 // thread. thread_count is accepted for signature compatibility and ignored (device grid).
 void render(const RenderEnv &ren, const PointProc &pointproc, int thread_count, int device = 0);
 // Fast path of the three stock callers: render() + the putpoint quantiser (main.rs:148-152).
 void render_rgb8(const RenderEnv &ren, uint8_t *data, int device = 0);
-// render_frames(), render.rs:926-989
-void render_frames(RenderEnv &ren, size_t width, size_t height,
-                   const std::function<void(int, const std::vector<uint8_t> &)> &frame_proc, int thread_count, int device = 0);
+// render_frames(), render.rs:926-989. frame_proc(i, data, len) receives frame i as `&[u8]` (RGB8, len = 3*width*height),
+// in frame order, on the calling thread, exactly like the reference's FnMut(i32, &[u8]). Unlike the reference the frames
+// are pipelined: all camera poses are interpolated first, then frames are dealt round-robin to `devices` (empty = every
+// visible GPU) with two page-locked frames in flight per GPU (rr_render_rgb8_async), so while frame_proc encodes frame k
+// the kernels and copies of the next frames are already running. width/height must equal ren.xres/yres (the reference's
+// putpoint would panic on a mismatch); RenderError otherwise.
+using FrameProc = std::function<void(int, const uint8_t *, size_t)>;
+void render_frames(RenderEnv &ren, size_t width, size_t height, const FrameProc &frame_proc, int thread_count,
+                   const std::vector<int> &devices = {});
+// the camera poses render_frames() renders, in order (exposed for tests and tools)
+std::vector<Camera> interpolate_camera_motion(const RenderEnv &ren, bool verbose = false);
 
 // built-in scene of main.rs:154-276 and the synthetic scene of BASELINE configs[3]
 RenderEnv default_scene(int width, int height, bool use_raymarching, bool glow_some, float glow_value);

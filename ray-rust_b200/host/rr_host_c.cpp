@@ -1,6 +1,9 @@
 // rr_host_c.cpp — small extern "C" facade over the C++ host layer so the Python tests can drive it
 // (scene construction, YAML round trips, flattening) without a GPU.
+#include <chrono>
 #include <cstring>
+
+#include <zlib.h>
 
 #include "rr_host.hpp"
 
@@ -91,5 +94,66 @@ int rrh_png_roundtrip(const uint8_t *rgb, uint32_t w, uint32_t h, const char *pa
         g_err = e.what();
         return -1;
     }
+}
+
+// PNG encode alone (image::save_buffer's share of main.rs:316-348): best-of-reps milliseconds and the encoded size.
+int rrh_png_encode_ms(const uint8_t *rgb, uint32_t w, uint32_t h, int reps, double *ms_best, uint64_t *png_bytes) {
+    try {
+        double best = 1e300;
+        size_t n = 0;
+        for (int r = 0; r < (reps < 1 ? 1 : reps); ++r) {
+            auto t0 = std::chrono::steady_clock::now();
+            std::vector<uint8_t> png = rr::encode_png_rgb8(rgb, w, h);
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            best = ms < best ? ms : best;
+            n = png.size();
+        }
+        *ms_best = best;
+        *png_bytes = n;
+        return 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+// render_frames (render.rs:926-989) of the handle's camera_motion over `n_devices` GPUs (0 = all).
+// mode 0: frames are only checksummed (CRC-32 of each frame into crcs[i], up to max_crcs), 1: each frame is PNG-encoded
+// in memory like the CLI does before writing it. Returns the number of frames, wall seconds in *seconds.
+int rrh_render_frames(void *h, int mode, int n_devices, double *seconds, uint32_t *crcs, int max_crcs) {
+    try {
+        Handle *H = (Handle *)h;
+        std::vector<int> devices;
+        for (int d = 0; d < n_devices; ++d) devices.push_back(d);
+        int frames = 0;
+        const uint32_t w = (uint32_t)H->ren.xres, hh = (uint32_t)H->ren.yres;
+        const rr::Camera saved = H->ren.camera;
+        auto t0 = std::chrono::steady_clock::now();
+        rr::render_frames(H->ren, w, hh, [&](int i, const uint8_t *data, size_t len) {
+            if (mode == 1) {
+                std::vector<uint8_t> png = rr::encode_png_rgb8(data, w, hh);
+                if (crcs && i < max_crcs) crcs[i] = (uint32_t)png.size();
+            } else if (crcs && i < max_crcs) {
+                crcs[i] = (uint32_t)crc32(0L, data, (uInt)len);
+            }
+            frames = i + 1;
+        }, 0, devices);
+        *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        H->ren.camera = saved;
+        return frames;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+// camera poses of render_frames(): 7 floats per frame (position xyz, rotation xyzw); returns the frame count
+int rrh_camera_motion(void *h, float *out, int max_frames) {
+    Handle *H = (Handle *)h;
+    const std::vector<rr::Camera> cams = rr::interpolate_camera_motion(H->ren, false);
+    for (size_t i = 0; i < cams.size() && (int)i < max_frames; ++i) {
+        float *o = out + 7 * i;
+        o[0] = cams[i].position.x; o[1] = cams[i].position.y; o[2] = cams[i].position.z;
+        o[3] = cams[i].rotation.x; o[4] = cams[i].rotation.y; o[5] = cams[i].rotation.z; o[6] = cams[i].rotation.w;
+    }
+    return (int)cams.size();
 }
 }

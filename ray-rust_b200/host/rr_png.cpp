@@ -1,15 +1,17 @@
 // rr_png.cpp — PNG output (image::save_buffer(.., Rgb8), main.rs:325-340) and texture input
 // (image::open for RenderMaterial.texture, render.rs:165-181, 215) on top of zlib.
-// Writer: 8-bit RGB, non-interlaced, filter 0, one deflate stream. Reader: returns an image only
+// Writer: 8-bit RGB, non-interlaced, filter 1 (Sub), one zlib stream deflated in parallel stripes. Reader: returns an image only
 // when it decodes to 8-bit RGB (colour type 2, or a palette without transparency, which the image
 // crate expands to Rgb8); everything else yields nullptr because the path honours only
 // DynamicImage::ImageRgb8 (render.rs:251).
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <thread>
 
 #include "rr_host.hpp"
@@ -51,40 +53,59 @@ std::vector<uint8_t> encode_png_rgb8(const uint8_t *rgb, uint32_t w, uint32_t h)
     unsigned hw = std::thread::hardware_concurrency();
     int nt = (int)std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)32, (size_t)std::max<uint32_t>(1, h / 64)});
     if (const char *e = getenv("RR_PNG_THREADS")) nt = std::max(1, atoi(e));
+    // four stripes per thread, handed out by a counter: sky rows deflate several times faster than rows full of spheres,
+    // equal row counts per thread would leave most threads waiting for the slowest stripe
+    const int ns = (int)std::min<uint32_t>((uint32_t)nt * 4u, std::max<uint32_t>(1, h / 16));
     struct Stripe {
         std::vector<uint8_t> z;
         uLong adler = 1, len = 0;
         bool ok = false;
     };
-    std::vector<Stripe> stripes(nt);
-    auto work = [&](int k) {
-        const uint32_t y0 = (uint32_t)((uint64_t)h * k / nt), y1 = (uint32_t)((uint64_t)h * (k + 1) / nt);
-        std::vector<uint8_t> raw((row + 1) * (y1 - y0));
-        for (uint32_t y = y0; y < y1; ++y) {
-            raw[(row + 1) * (y - y0)] = 0;  // filter type 0
-            memcpy(&raw[(row + 1) * (y - y0) + 1], rgb + row * y, row);
+    std::vector<Stripe> stripes(ns);
+    std::atomic<int> next{0};
+    auto work = [&]() {
+        std::unique_ptr<uint8_t[]> raw;  // not zero-filled
+        size_t raw_cap = 0;
+        for (int k; (k = next.fetch_add(1)) < ns;) {
+            const uint32_t y0 = (uint32_t)((uint64_t)h * k / ns), y1 = (uint32_t)((uint64_t)h * (k + 1) / ns);
+            const size_t raw_len = (row + 1) * (y1 - y0);
+            if (raw_len > raw_cap) { raw.reset(new uint8_t[raw_len]); raw_cap = raw_len; }
+            for (uint32_t y = y0; y < y1; ++y) {
+                // filter type 1 (Sub: byte - byte of the pixel to the left). On rendered frames zlib level 1 then runs 1.5x
+                // faster and the file is 40 % smaller than with filter 0 (measured: 4K default scene, 143 vs 96 MB/s per
+                // thread, 9.7 % vs 16.1 % of the raw size); the filter itself is one pass fused into the copy.
+                uint8_t *o = &raw[(row + 1) * (y - y0)];
+                const uint8_t *in = rgb + row * y;
+                o[0] = 1;
+                for (size_t i = 0; i < row && i < 3; ++i) o[1 + i] = in[i];
+                for (size_t i = 3; i < row; ++i) o[1 + i] = (uint8_t)(in[i] - in[i - 3]);
+            }
+            Stripe &s = stripes[k];
+            s.len = (uLong)raw_len;
+            s.adler = adler32(1L, raw.get(), (uInt)raw_len);
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (deflateInit2(&zs, 1, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) continue;
+            s.z.resize(deflateBound(&zs, (uLong)raw_len) + 16);
+            zs.next_in = raw.get(); zs.avail_in = (uInt)raw_len;
+            zs.next_out = s.z.data(); zs.avail_out = (uInt)s.z.size();
+            const int rc = deflate(&zs, k == ns - 1 ? Z_FINISH : Z_SYNC_FLUSH);
+            s.ok = (k == ns - 1) ? rc == Z_STREAM_END : (rc == Z_OK && zs.avail_in == 0);
+            s.z.resize(zs.total_out);
+            deflateEnd(&zs);
         }
-        Stripe &s = stripes[k];
-        s.len = (uLong)raw.size();
-        s.adler = adler32(1L, raw.data(), (uInt)raw.size());
-        z_stream zs;
-        memset(&zs, 0, sizeof zs);
-        if (deflateInit2(&zs, 1, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return;
-        s.z.resize(deflateBound(&zs, (uLong)raw.size()) + 16);
-        zs.next_in = raw.data(); zs.avail_in = (uInt)raw.size();
-        zs.next_out = s.z.data(); zs.avail_out = (uInt)s.z.size();
-        const int rc = deflate(&zs, k == nt - 1 ? Z_FINISH : Z_SYNC_FLUSH);
-        s.ok = (k == nt - 1) ? rc == Z_STREAM_END : (rc == Z_OK && zs.avail_in == 0);
-        s.z.resize(zs.total_out);
-        deflateEnd(&zs);
     };
     std::vector<std::thread> th;
-    for (int k = 1; k < nt; ++k) th.emplace_back(work, k);
-    work(0);
+    for (int k = 1; k < nt; ++k) th.emplace_back(work);
+    work();
     for (auto &t : th) t.join();
+    const int nt_total = ns;
     std::vector<uint8_t> z = {0x78, 0x01};  // zlib header: deflate, 32K window, fastest
     uLong adler = 1;
-    for (int k = 0; k < nt; ++k) {
+    size_t zbytes = 6;
+    for (int k = 0; k < nt_total; ++k) zbytes += stripes[k].z.size();
+    z.reserve(zbytes);
+    for (int k = 0; k < nt_total; ++k) {
         if (!stripes[k].ok) throw std::runtime_error("png: deflate failed");
         z.insert(z.end(), stripes[k].z.begin(), stripes[k].z.end());
         adler = k == 0 ? stripes[k].adler : adler32_combine(adler, stripes[k].adler, (z_off_t)stripes[k].len);
@@ -137,6 +158,11 @@ std::shared_ptr<TextureRgb8> load_png_rgb8(const std::string &path) {
     else if (ctype == 3 && depth == 8 && !trns && !plte.empty()) channels = 1;
     else return nullptr;  // Luma / RGBA / 16-bit: not ImageRgb8, the path would ignore it
     const size_t stride = (size_t)w * channels;
+    // The header comes from a file named by an untrusted scene YAML: refuse sizes the IDAT data cannot possibly inflate
+    // to (deflate expands at most ~1032:1) or that are absurd for a texture, BEFORE allocating (nullptr = "not an RGB8
+    // image", like every other failed load).
+    const unsigned long long need = ((unsigned long long)stride + 1) * h;
+    if (need > (1ull << 31) || need > (unsigned long long)idat.size() * 1040ull + 65536ull) return nullptr;
     std::vector<uint8_t> raw((stride + 1) * h);
     uLongf rawlen = (uLongf)raw.size();
     if (uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size()) != Z_OK || rawlen != raw.size()) return nullptr;

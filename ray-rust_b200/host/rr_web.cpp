@@ -5,7 +5,8 @@
 //   anything else                           -> 404 "empty"
 // The reference clones the whole RenderEnv per request (webserver.rs:268) and renders on a tokio worker; here every
 // request only patches the camera fields of rr_frame_params and renders on the ONE resident scene handle, which is
-// safe to call from concurrent connection threads (per-handle mutex in the C ABI).
+// safe to call from concurrent connection threads: the C ABI runs up to four renders of one handle at a time on separate
+// lanes (stream pair + device frame), and each request renders into a page-locked frame from a small pool.
 #include <arpa/inet.h>
 #include <netinet/in.h>
 #include <sys/socket.h>
@@ -16,6 +17,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <memory>
+#include <mutex>
 #include <sstream>
 #include <thread>
 
@@ -77,10 +80,32 @@ void respond(int fd, int code, const char *status, const char *ctype, const void
     send_all(fd, body, n);
 }
 
+// Page-locked frames shared by the connection threads (at most as many as requests are in flight at once).
+struct FramePool {
+    std::mutex mu;
+    std::vector<std::unique_ptr<PinnedFrame>> free_;
+    std::unique_ptr<PinnedFrame> take(size_t bytes) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (!free_.empty()) {
+                auto f = std::move(free_.back());
+                free_.pop_back();
+                return f;
+            }
+        }
+        try { return std::unique_ptr<PinnedFrame>(new PinnedFrame(bytes ? bytes : 1)); } catch (...) { return nullptr; }
+    }
+    void give(std::unique_ptr<PinnedFrame> f) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (free_.size() < 8) free_.push_back(std::move(f));
+    }
+};
+
 struct Server {
     const RenderEnv *ren;
     int width, height, device;
     rr_scene *handle;
+    FramePool *pool;
 };
 
 void handle_conn(int fd, const Server *srv) {
@@ -133,11 +158,15 @@ void handle_conn(int fd, const Server *srv) {
         p.xres = srv->width; p.yres = srv->height;
         p.cam_position[0] = xpos; p.cam_position[1] = ypos; p.cam_position[2] = zpos;
         p.cam_rotation[0] = rot.x; p.cam_rotation[1] = rot.y; p.cam_rotation[2] = rot.z; p.cam_rotation[3] = rot.w;
-        std::vector<uint8_t> data((size_t)3 * srv->width * srv->height);
-        if (rr_render_rgb8(srv->handle, &p, data.data(), 0) == RR_OK) {
-            std::vector<uint8_t> png = encode_png_rgb8(data.data(), (uint32_t)srv->width, (uint32_t)srv->height);
+        // a page-locked frame from the server's pool (reused across requests): asynchronous D2H at the full PCIe rate
+        std::unique_ptr<PinnedFrame> data = srv->pool->take((size_t)3 * srv->width * srv->height);
+        const bool ok = data && rr_render_rgb8(srv->handle, &p, data->data(), 0) == RR_OK;
+        if (ok) {
+            std::vector<uint8_t> png = encode_png_rgb8(data->data(), (uint32_t)srv->width, (uint32_t)srv->height);
+            srv->pool->give(std::move(data));
             respond(fd, 200, "OK", "image/png", png.data(), png.size(), true);
         } else {
+            if (data) srv->pool->give(std::move(data));
             const std::string msg = std::string("fail to render: ") + rr_last_error();
             respond(fd, 500, "Internal Server Error", "text/plain", msg.data(), msg.size());
         }
@@ -152,7 +181,8 @@ void handle_conn(int fd, const Server *srv) {
 
 // run_webserver, webserver.rs:324-333. Blocks forever (until the process is killed), like the reference.
 int run_webserver(const RenderEnv &ren, int width, int height, int port, int device) {
-    Server srv{&ren, width, height, device, nullptr};
+    FramePool pool;
+    Server srv{&ren, width, height, device, nullptr, &pool};
     FlatScene flat = flatten(ren);
     rr_scene_desc desc = flat.desc();
     if (rr_scene_create(&desc, device, &srv.handle) != RR_OK)

@@ -86,9 +86,11 @@ void flatten(const rr_scene_desc *d, Flat &f) {
     }
     H.n_glow_head = ng;
     fill_march_bounds(H, (int)f.sph.size() < RR_HEAD_SPHERES ? (int)f.sph.size() : RR_HEAD_SPHERES);
+    fill_head_pairs(H, (int)f.sph.size() < RR_HEAD_SPHERES ? (int)f.sph.size() : RR_HEAD_SPHERES,
+                    (int)f.flo_o.size() < RR_HEAD_FLOORS ? (int)f.flo_o.size() : RR_HEAD_FLOORS);
 }
 
-FrameParams to_dev(const rr_frame_params *p) {
+FrameParams to_dev(const rr_frame_params *p, const SceneHead &H) {
     FrameParams d{};
     d.xres = p->xres; d.yres = p->yres; d.xfov = p->xfov; d.yfov = p->yfov;
     for (int k = 0; k < 3; ++k) { d.cam_pos[k] = p->cam_position[k]; d.light[k] = p->light[k]; }
@@ -96,6 +98,7 @@ FrameParams to_dev(const rr_frame_params *p) {
     d.use_raymarching = p->use_raymarching; d.glow_enabled = p->glow_enabled; d.glow_effect = p->glow_effect;
     d.max_reflections = p->max_reflections; d.max_refractions = p->max_refractions; d.bg_kind = p->bg_kind;
     d.band_count = 1; d.band_rows = 1; d.band_index = 0; d.local_rows = p->yres; d.row0 = 0; d.placed = 0;
+    finish_frame_params(d, H);
     return d;
 }
 }  // namespace
@@ -105,12 +108,12 @@ extern "C" int hostsim_render_f32_ex(const rr_scene_desc *desc, const rr_frame_p
                                      int culling, int *used_bvh) {
     Flat f;
     flatten(desc, f);
-    FrameParams P = to_dev(params);
+    FrameParams P = to_dev(params, f.H);
     Counters cnt{};
     SceneView S{};
     S.sph = f.G.sph; S.sph_oi = f.G.sph_oi; S.flo_o = f.G.flo_o; S.flo_n = f.G.flo_n; S.flo_oi = f.G.flo_oi;
     S.n_spheres = f.G.n_spheres; S.n_floors = f.G.n_floors;
-    const bool bvh = culling && f.G.n_bvh_nodes > 0;
+    const bool bvh = (culling & 1) && f.G.n_bvh_nodes > 0;
     S.bvh_a = f.G.bvh_a; S.bvh_b = f.G.bvh_b; S.bvh_w = f.G.bvh_w; S.bsph = f.G.bsph; S.bsph_oi = f.G.bsph_oi;
     S.n_bvh_nodes = bvh ? f.G.n_bvh_nodes : 0;
     if (used_bvh) *used_bvh = bvh ? 1 : 0;
@@ -118,7 +121,7 @@ extern "C" int hostsim_render_f32_ex(const rr_scene_desc *desc, const rr_frame_p
     M.sph = f.G.sph_m; M.sph_glow = f.G.sph_glow; M.sph_oi = f.G.sph_oi; M.flo_o = f.G.flo_o; M.flo_n = f.G.flo_n; M.flo_oi = f.G.flo_oi;
     M.n_spheres = f.G.n_spheres; M.n_floors = f.G.n_floors;
     const int glow = !(P.glow_enabled && f.G.n_glow > 0) ? 0 : (f.H.n_glow_head >= 0 ? 1 : 2);
-    const bool mbvh = P.use_raymarching && culling && f.G.n_bvh_nodes > 0 && glow != 2;  // as launch_two (rr_march.cu)
+    const bool mbvh = P.use_raymarching && (culling & 1) && f.G.n_bvh_nodes > 0 && glow != 2;  // as launch_two (rr_march.cu)
     M.bvh_a = f.G.bvh_a; M.bvh_b = f.G.bvh_b; M.bsph = f.G.bsph_m; M.bsph_oi = f.G.bsph_oi; M.n_bvh_nodes = f.G.n_bvh_nodes;
     M.scene_abs = 0.0f;
     for (int k = 0; k < 3; ++k) M.scene_abs = fmaxf(M.scene_abs, fmaxf(fabsf(f.G.scene_lo[k]), fabsf(f.G.scene_hi[k])));
@@ -126,7 +129,12 @@ extern "C" int hostsim_render_f32_ex(const rr_scene_desc *desc, const rr_frame_p
     for (int iy = 0; iy < P.yres; ++iy)
         for (int ix = 0; ix < P.xres; ++ix) {
             V3 c;
-            if (!P.use_raymarching) c = bvh ? trace_pixel<true, true>(f.G, f.H, S, P, ix, iy, cnt) : trace_pixel<true, false>(f.G, f.H, S, P, ix, iy, cnt);
+            // the device picks the head-only instance for scenes that fit the SceneHead (rr_trace.cu launch_tw); `culling & 2`
+            // forces the general instance so that both are compared with the oracle
+            const bool headonly = !bvh && !(culling & 2) && f.G.n_floors <= RR_HEAD_FLOORS && f.G.n_spheres <= RR_HEAD_SPHERES;
+            if (!P.use_raymarching) c = bvh ? trace_pixel<true, true>(f.G, f.H, S, P, ix, iy, cnt)
+                                      : headonly ? trace_pixel<true, false, true>(f.G, f.H, S, P, ix, iy, cnt)
+                                                 : trace_pixel<true, false>(f.G, f.H, S, P, ix, iy, cnt);
             else if (mbvh && glow == 0) c = march_pixel<true, 0, true>(f.G, f.H, M, P, ix, iy, cnt);
             else if (mbvh) c = march_pixel<true, 1, true>(f.G, f.H, M, P, ix, iy, cnt);
             else if (glow == 0) c = march_pixel<true, 0>(f.G, f.H, M, P, ix, iy, cnt);

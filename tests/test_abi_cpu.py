@@ -59,6 +59,21 @@ def test_missing_library_fails_loudly(rr, monkeypatch):
         f.load()
 
 
+def test_library_is_built_from_the_sources_next_to_it(rr):
+    """Built files are not in git history but travel to the GPU box: the hash of csrc/ + include/rr_ffi.h + the nvcc flags
+    is compiled into the library, and the loader rebuilds a binary whose hash differs (ray-rust_b200/build.py)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("rr_build", os.path.join(ROOT, "ray-rust_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    lib = rr.ffi.load()
+    info = lib.rr_build_info().decode()
+    assert info.startswith("rr_src_hash=") and "sm_100a" in info and "fmad=false" in info
+    assert info.split()[0] == "rr_src_hash=" + b.source_hash() == "rr_src_hash=" + b.embedded_hash()
+    assert b.source_hash(["-DX"]) != b.source_hash()
+
+
 def test_error_convention_without_device(rr):
     """Without a GPU every entry point must fail with a status code and a message, not crash."""
     import torch

@@ -11,6 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = os.path.join(ROOT, "ray-rust_b200", "host")
 CLI = os.path.join(HOST, "ray-rust")
+HOSTLIB = os.path.join(HOST, "libray_rust_host.so")
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -119,6 +120,11 @@ def test_cli_camera_motion_render_frames(rr, oracle, tmp_path):
     # oracle side: interpolate the camera exactly like render.rs:907-970 (f32) and render each frame
     f32 = np.float32
     lib = oracle.load()
+    import ctypes.util
+
+    libm = C.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    libm.atan2f.restype = C.c_float
+    libm.atan2f.argtypes = [C.c_float, C.c_float]
 
     def hermite(t, x0, x1, v0, v1):
         h = f32(1.0)
@@ -149,14 +155,65 @@ def test_cli_camera_motion_render_frames(rr, oracle, tmp_path):
                 lib.oracle_quat_slerp(oracle.fa(*prev_rot), oracle.fa(*krot), float(f), out)
                 rot = [f32(x) for x in out]
             else:
-                rot = None  # look-at goes through atan2f on the host; checked loosely below
-            if rot is not None:
-                e = rr.default_scene(160, 90)
-                e.camera.position = tuple(pos)
-                e.camera.rotation = rr.Quat(*rot)
-                _close(frames[k], oracle.render(e)["u8"], 0.999)
-            else:
-                assert frames[k].std() > 10  # a real image, not a blank frame
+                # look-at, render.rs:961-967 restated in f32 with libm's atan2f/sinf/cosf (what Rust's f32 methods call)
+                tgt = v3(key["camera_target"])
+                dx, dy, dz = tgt[0] - pos[0], tgt[1] - pos[1], tgt[2] - pos[2]
+                pitch = f32(libm.atan2f(float(dy), float(np.sqrt(dx * dx + dz * dz))))
+                yaw = -f32(libm.atan2f(float(dz), float(dx)))
+                q = rr.Quat.rotation(yaw, 0.0, 1.0, 0.0).mul(rr.Quat.rotation(pitch, 0.0, 0.0, 1.0)).mul(
+                    rr.Quat.rotation(-f32(np.pi) / f32(2.0), 1.0, 0.0, 0.0))
+                rot = list(q.as_tuple())
+            e = rr.default_scene(160, 90)
+            e.camera.position = tuple(pos)
+            e.camera.rotation = rr.Quat(*rot)
+            _close(frames[k], oracle.render(e)["u8"], 0.999)
             k += 1
         prev_pos, prev_rot, prev_vel = kpos, krot, v1
     assert not np.array_equal(frames[0], frames[1])
+
+
+def test_render_frames_pipeline_equals_single_frames(rr, tmp_path):
+    """render_frames (render.rs:926-989) deals frames to lanes / GPUs and keeps several in flight; every frame must be
+    byte-identical to rendering that camera pose alone, in order, whatever the number of devices."""
+    import ctypes as C
+    import zlib
+
+    import torch
+    import yaml
+
+    lib = C.CDLL(HOSTLIB)
+    lib.rrh_env_new.restype = C.c_void_p
+    lib.rrh_env_new.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_uint64]
+    lib.rrh_env_free.argtypes = [C.c_void_p]
+    lib.rrh_env_deserialize.argtypes = [C.c_void_p, C.c_char_p]
+    lib.rrh_render_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.c_int]
+    lib.rrh_camera_motion.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
+    w, h = 320, 180
+    ren = rr.default_scene(w, h)
+    doc = yaml.safe_load(ren.serialize())
+    doc["camera_motion"] = [
+        {"camera": {"position": {"x": 40.0, "y": -120.0, "z": -280.0}, "pyr": {"x": 0.1, "y": -1.4, "z": -1.5707964}},
+         "velocity": {"x": 10.0, "y": 0.0, "z": 5.0}, "camera_target": None, "duration": 3.5},
+        {"camera": {"position": {"x": 80.0, "y": -100.0, "z": -260.0}, "pyr": {"x": 0.0, "y": -1.2, "z": -1.5707964}},
+         "velocity": {"x": 0.0, "y": 0.0, "z": 0.0}, "camera_target": {"x": 0.0, "y": -30.0, "z": 172.0}, "duration": 2.0},
+    ]
+    env = lib.rrh_env_new(0, w, h, 0, 0, 0.0, 0, 0)
+    assert env and lib.rrh_env_deserialize(env, yaml.safe_dump(doc).encode()) == 0
+    poses = (C.c_float * (7 * 32))()
+    n = lib.rrh_camera_motion(env, poses, 32)
+    assert n == 11  # int(3.5 / 0.5) + int(2.0 / 0.5)
+    scene = rr.DeviceScene(ren, 0)
+    want = []
+    for i in range(n):
+        p = ren.frame_params()
+        p.cam_position[:] = poses[7 * i:7 * i + 3]
+        p.cam_rotation[:] = poses[7 * i + 3:7 * i + 7]
+        want.append(zlib.crc32(scene.render_rgb8(p).tobytes()))
+    scene.close()
+    assert len(set(want)) == n
+    for ndev in sorted({1, min(2, torch.cuda.device_count()), torch.cuda.device_count()}):
+        crcs = (C.c_uint32 * 32)()
+        sec = C.c_double()
+        assert lib.rrh_render_frames(env, 0, ndev, C.byref(sec), crcs, 32) == n
+        assert list(crcs[:n]) == want, f"{ndev} device(s)"
+    lib.rrh_env_free(env)

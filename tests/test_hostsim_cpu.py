@@ -30,14 +30,14 @@ def hostsim(rr):
 
     lib.hostsim_render_f32_ex.argtypes = lib.hostsim_render_f32.argtypes + [C.c_int, C.POINTER(C.c_int)]
 
-    def render(ren, culling=False):
+    def render(ren, culling=False, general=False):
         flat = ren.flatten()
         p = ren.frame_params()
         out = np.empty((p.yres, p.xres, 3), dtype=np.float32)
         cnt = rr.ffi.rr_ray_counts()
         used = C.c_int(0)
         assert lib.hostsim_render_f32_ex(C.byref(flat.desc), C.byref(p), out.ctypes.data_as(C.c_void_p), C.byref(cnt),
-                                         1 if culling else 0, C.byref(used)) == 0
+                                         (1 if culling else 0) | (2 if general else 0), C.byref(used)) == 0
         if culling:
             assert used.value == 1, "the builder produced no tree for this scene"
         return out, cnt
@@ -45,9 +45,9 @@ def hostsim(rr):
     return render
 
 
-def _check(ren, oracle, hostsim, culling=False):
+def _check(ren, oracle, hostsim, culling=False, general=False):
     ref = oracle.render(ren, threads=os.cpu_count() or 1, want_f32=True, want_tags=True, want_counts=True)
-    out, cnt = hostsim(ren, culling)
+    out, cnt = hostsim(ren, culling, general)
     # same libm on both sides here, so even bgcolor / glow pixels must agree bit for bit
     a, b = out.view(np.uint32), ref["f32"].view(np.uint32)
     nan = np.isnan(out)
@@ -59,6 +59,20 @@ def _check(ren, oracle, hostsim, culling=False):
 @pytest.mark.parametrize("march", [False, True])
 def test_default_scene_logic(rr, oracle, hostsim, march):
     _check(rr.default_scene(96, 72, use_raymarching=march, glow_effect=1.0 if march else None), oracle, hostsim)
+
+
+def test_default_scene_general_instance(rr, oracle, hostsim):
+    """The built-in scene fits the SceneHead, so the device renders it with the head-only instance (no count checks, no
+    tail loops, padded never-hit slots); the general instance must give the same bits."""
+    _check(rr.default_scene(96, 72), oracle, hostsim, general=True)
+
+
+@pytest.mark.parametrize("n_spheres", [0, 1, 2, 3, 4, 5, 7])
+def test_head_sizes_logic(rr, oracle, hostsim, n_spheres):
+    """Sphere counts around the head size: odd pairs, padded slots, a tail of one; head-only and general instance."""
+    ren = rr.synthetic_scene(48, 32, n_spheres=n_spheres, seed=11 + n_spheres)
+    _check(ren, oracle, hostsim)
+    _check(ren, oracle, hostsim, general=True)
 
 
 def test_synthetic_scene_logic(rr, oracle, hostsim):

@@ -160,20 +160,23 @@ def test_fence_signal_memset_read(rr):
     rr.ffi.check(lib.rr_device_free(0, p))
 
 
-def test_overlapping_launches_of_one_handle(rr):
-    """Kernels of ONE scene handle queued on several streams run concurrently; each launch owns one of 16 (tile queue,
-    block counter) slots that reset themselves, so 12 overlapping launches on 6 streams must all produce the frame."""
+@pytest.mark.parametrize("march", [False, True])
+def test_overlapping_launches_of_one_handle(rr, march):
+    """Kernels of ONE scene handle queued on several streams run concurrently; each launch (ray-trace AND ray-march mode)
+    owns one of 64 (tile queue, block counter) slots that reset themselves, so 12 overlapping launches on 6 streams must
+    all produce the frame, and the slot ring must survive wrapping."""
     import torch
 
-    ren = rr.default_scene(1024, 576)
+    w, h = (1024, 576) if not march else (512, 288)
+    ren = rr.default_scene(w, h, use_raymarching=march, glow_effect=1.0 if march else None)
     scene = rr.DeviceScene(ren, 0)
     p = ren.frame_params()
-    ref = torch.empty(576 * 1024 * 3, dtype=torch.uint8, device="cuda:0")
+    ref = torch.empty(h * w * 3, dtype=torch.uint8, device="cuda:0")
     scene.render_rgb8_device(p, ref.data_ptr())
     torch.cuda.synchronize()
     streams = [torch.cuda.Stream() for _ in range(6)]
     bufs = [torch.zeros_like(ref) for _ in range(12)]
-    for rep in range(3):                                   # 36 launches in total: the slot ring wraps twice
+    for rep in range(7 if not march else 3):               # 84 launches: the 64-slot ring wraps
         for b in bufs:
             b.zero_()
         torch.cuda.synchronize()
@@ -182,6 +185,84 @@ def test_overlapping_launches_of_one_handle(rr):
         torch.cuda.synchronize()
         for b in bufs:
             assert torch.equal(b, ref)
+    scene.close()
+
+
+@pytest.mark.parametrize("march", [False, True])
+def test_concurrent_host_renders_of_one_handle(rr, march):
+    """Eight host threads call the blocking rr_render_rgb8 on ONE handle (the web server's situation,
+    webserver.rs:268-280): the handle runs up to four of them at a time on separate lanes; all frames must be right."""
+    import threading
+
+    w, h = 640, 360
+    ren = rr.default_scene(w, h, use_raymarching=march, glow_effect=1.0 if march else None)
+    scene = rr.DeviceScene(ren, 0)
+    views = []
+    for k in range(8):
+        r = rr.default_scene(w, h, use_raymarching=march, glow_effect=1.0 if march else None)
+        r.camera.position = np.asarray((0.0, -150.0 + 10.0 * k, -300.0 + 7.0 * k), dtype=np.float32)
+        views.append(r.frame_params())
+    ref = [scene.render_rgb8(v).copy() for v in views]
+    assert not np.array_equal(ref[0], ref[7])
+    out = [None] * 8
+    err = []
+
+    def work(k):
+        try:
+            for _ in range(3):
+                out[k] = scene.render_rgb8(views[k])
+        except Exception as e:  # noqa: BLE001
+            err.append(e)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not err
+    for k in range(8):
+        assert np.array_equal(out[k], ref[k])
+    scene.close()
+
+
+def test_async_submit_wait(rr):
+    """rr_render_rgb8_async / rr_render_wait (render_frames support): several frames of one handle in flight, waited for
+    out of order; a fifth submission waits for a lane; stale tickets are rejected."""
+    lib = rr.ffi.load()
+    w, h = 800, 448
+    ren = rr.default_scene(w, h)
+    scene = rr.DeviceScene(ren, 0)
+    n = 6
+    views, hosts, tickets = [], [], []
+    for k in range(n):
+        r = rr.default_scene(w, h)
+        r.camera.position = np.asarray((0.0, -150.0 + 12.0 * k, -300.0), dtype=np.float32)
+        views.append(r.frame_params())
+        ptr = C.c_void_p()
+        rr.ffi.check(lib.rr_host_alloc(w * h * 3, C.byref(ptr)))
+        hosts.append(ptr)
+    ref = [scene.render_rgb8(v).copy() for v in views]
+    for k in range(4):
+        t = C.c_int32(-1)
+        rr.ffi.check(lib.rr_render_rgb8_async(scene.handle, C.byref(views[k]), hosts[k], 0, C.byref(t)))
+        assert t.value >= 0
+        tickets.append(t.value)
+    ms = C.c_float()
+    for k in (2, 0):                                        # out of order
+        rr.ffi.check(lib.rr_render_wait(scene.handle, tickets[k], C.byref(ms)))
+        assert ms.value > 0.0
+        assert lib.rr_render_wait(scene.handle, tickets[k], None) == rr.ffi.RR_ERR_BAD_ARG   # waited for twice
+    for k in (4, 5):                                        # lanes freed above are reused
+        t = C.c_int32(-1)
+        rr.ffi.check(lib.rr_render_rgb8_async(scene.handle, C.byref(views[k]), hosts[k], 0, C.byref(t)))
+        tickets.append(t.value)
+    for k in (1, 3, 4, 5):
+        rr.ffi.check(lib.rr_render_wait(scene.handle, tickets[k], None))
+    for k in range(n):
+        got = np.frombuffer(C.string_at(hosts[k], w * h * 3), dtype=np.uint8).reshape(h, w, 3)
+        assert np.array_equal(got, ref[k])
+        lib.rr_host_free(hosts[k])
+    assert lib.rr_render_wait(scene.handle, 12345, None) == rr.ffi.RR_ERR_BAD_ARG
     scene.close()
 
 

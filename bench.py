@@ -686,9 +686,9 @@ def host_path(c):
         ren = rr.default_scene(w, h)
         doc = yaml.safe_load(ren.serialize())
         doc["camera_motion"] = [
-            {"camera": {"position": {"x": 60.0, "y": -120.0, "z": -280.0}, "pyr": doc["camera"]["pyr"]},
+            {"camera": {"position": {"x": 60.0, "y": -120.0, "z": -280.0}, "pyr": dict(doc["camera"]["pyr"])},
              "velocity": {"x": 10.0, "y": 0.0, "z": 5.0}, "camera_target": {"x": 0.0, "y": -30.0, "z": 172.0}, "duration": 6.0},
-            {"camera": {"position": {"x": 120.0, "y": -60.0, "z": -240.0}, "pyr": doc["camera"]["pyr"]},
+            {"camera": {"position": {"x": 120.0, "y": -60.0, "z": -240.0}, "pyr": dict(doc["camera"]["pyr"])},
              "velocity": {"x": 0.0, "y": 0.0, "z": 0.0}, "camera_target": None, "duration": 6.0},
         ]
         env = hl.rrh_env_new(0, w, h, 0, 0, 0.0, 0, 0)
@@ -696,11 +696,20 @@ def host_path(c):
             continue
         for mode, key in ((0, "frames_per_s"), (1, "frames_per_s_with_png_encode")):
             sec = C.c_double()
-            hl.rrh_render_frames(env, mode, 1, C.byref(sec), None, 0)  # warm-up (scene upload, pinned frames)
-            n = hl.rrh_render_frames(env, mode, 1, C.byref(sec), None, 0)
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)  # render_frames prints the reference's progress lines; stdout carries exactly one JSON line
+            try:
+                hl.rrh_render_frames(env, mode, 1, C.byref(sec), None, 0)  # warm-up (scene upload, pinned frames)
+                n = hl.rrh_render_frames(env, mode, 1, C.byref(sec), None, 0)
+            finally:
+                os.dup2(saved, 1)
+                os.close(saved)
             if n > 0:
                 out[f"render_frames_{tag}_{key}"] = n / sec.value
                 out[f"render_frames_{tag}_frames"] = n
+            else:
+                out[f"render_frames_{tag}_error"] = hl.rrh_last_error().decode("utf-8", "replace")
         hl.rrh_env_free(env)
     out["render_frames_note"] = ("render_frames (render.rs:926-989) on ONE GPU through rr_render_rgb8_async: two page-locked frames in flight, "
                                  "frame_proc = CRC-32 of the frame / in-memory PNG encode (what the CLI does before writing)")

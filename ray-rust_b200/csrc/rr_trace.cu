@@ -228,8 +228,8 @@ static cudaError_t launch_tw(const DevScene &G, const SceneHead &H, const FrameP
 
 // Tile shape (measured, profiles/r1_s2_tile_schedule.md): 128x1 macro tiles (four 32x1 sub-tiles, one 384-byte store)
 // whenever the frame allows it — they win locally too (4K 0.226 -> 0.217 ms, 8K 0.862 -> 0.807 ms: a quarter of the tile
-// bookkeeping and queue traffic, full-line stores) — except for the BVH instance rendering into local memory, whose
-// incoherent secondary rays want the 8x4 footprint; 32x1 row tiles for other placed frames; 8x4 otherwise.
+// bookkeeping and queue traffic, full-line stores) — except for the BVH instances, whose incoherent secondary rays want
+// the 8x4 footprint; 32x1 row tiles for other placed frames; 8x4 otherwise.
 template <bool COUNT, bool F32OUT, bool STAGE, bool BVH>
 static cudaError_t launch_one(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
                               Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, size_t smem, const Signal &sig) {
@@ -239,9 +239,13 @@ static cudaError_t launch_one(const DevScene &G, const SceneHead &H, const Frame
         // launches of the host pipeline (rr_render_rgb8) need the finer 8x4 granularity
         const long long macro_tiles = (long long)(P.xres / 128) * P.local_rows;
         const bool enough = macro_tiles >= 4ll * li.sm_count * (RR_TRACE_MIN_BLOCKS * TRACE_THREADS / 32);
-        if (wide && enough && (P.placed || !BVH) && P.xres % 128 == 0 && row_stride % 16 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0)
+        // BVH instances always keep the 8x4 footprint, placed or not: their incoherent secondary rays lose far more to a
+        // 128x1 / 32x1 footprint than the peer stores win (measured on 2 GPUs, 1 024 spheres at 4K: the placed step took
+        // 1.78 ms with 128x1 tiles against a 1.23 ms kernel with 8x4 tiles; at ~2 ms per 25 MB frame the NVLink store rate is
+        // irrelevant). This was the unexplained 0.53 efficiency of that scene on 8 GPUs in round 1.
+        if (wide && enough && !BVH && P.xres % 128 == 0 && row_stride % 16 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0)
             return launch_tw<COUNT, F32OUT, STAGE, BVH, 128>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem, sig);
-        if (P.placed && P.xres % 32 == 0)
+        if (P.placed && !BVH && P.xres % 32 == 0)
             return launch_tw<COUNT, F32OUT, STAGE, BVH, 32>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem, sig);
     }
     return launch_tw<COUNT, F32OUT, STAGE, BVH, 8>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem, sig);

@@ -199,6 +199,8 @@ void PinnedFrame::resize(size_t bytes) {
     n_ = bytes;
 }
 
+void upload_scene(const RenderEnv &ren, int device) { device_scene(ren, device); }
+
 void render(const RenderEnv &ren, const PointProc &pointproc, int /*thread_count*/, int device) {
     auto scene = device_scene(ren, device);
     rr_frame_params p = ren.frame_params();

@@ -206,6 +206,11 @@ private:
     size_t n_ = 0;
 };
 
+// Makes the scene resident on `device` now (CUDA context + flattened upload) instead of at the first render. The
+// reference builds its RenderEnv before it starts the "Rendering time" clock (main.rs:154-316); the CLI does the same
+// with the device copy of the scene.
+void upload_scene(const RenderEnv &ren, int device = 0);
+
 using PointProc = std::function<void(int, int, const RenderColor &)>;
 // render(), render.rs:801-805. Calls pointproc(x, y, colour) once per pixel, row-major, on the caller
 // thread. thread_count is accepted for signature compatibility and ignored (device grid).

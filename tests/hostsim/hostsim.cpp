@@ -154,3 +154,17 @@ extern "C" int hostsim_render_f32_ex(const rr_scene_desc *desc, const rr_frame_p
 extern "C" int hostsim_render_f32(const rr_scene_desc *desc, const rr_frame_params *params, float *out, rr_ray_counts *counts) {
     return hostsim_render_f32_ex(desc, params, out, counts, 0, nullptr);
 }
+
+// fmod_2pi() (rr_device.cuh) against fmodf over every float in [lo, hi): returns the number of mismatching arguments
+extern "C" long long hostsim_fmod_2pi_mismatches(float lo, float hi, float *first_bad) {
+    long long bad = 0;
+    const float y = 2.0f * PI_F;
+    for (float x = lo; x < hi; x = nextafterf(x, INFINITY)) {
+        const float a = fmod_2pi(x), b = fmodf(x, y);
+        if (memcmp(&a, &b, 4) != 0) {
+            if (bad == 0 && first_bad) *first_bad = x;
+            ++bad;
+        }
+    }
+    return bad;
+}

@@ -129,3 +129,15 @@ def test_march_bvh_logic(rr, oracle, hostsim):
     _check(rr.synthetic_scene(64, 36, n_spheres=300, use_raymarching=True), oracle, hostsim, culling=True)
     _check(rr.synthetic_scene(48, 27, n_spheres=1024, use_raymarching=True, glow_effect=0.7), oracle, hostsim, culling=True)
     _check(rr.synthetic_scene(40, 24, n_spheres=24, seed=11, use_raymarching=True, glow_effect=1.0), oracle, hostsim, culling=True)
+
+
+def test_fmod_2pi_is_fmodf(hostsim):
+    """bgcolor's fmodf(x, 2*pi) is replaced on the device by a three-instruction exact remainder (rr_device.cuh fmod_2pi):
+    identical bits for every float in [1, 1024) (bgcolor's arguments lie in [58, 256]) and the fmodf fallback outside."""
+    so = os.path.join(HS, "libhostsim.so")
+    lib = C.CDLL(so)
+    lib.hostsim_fmod_2pi_mismatches.restype = C.c_longlong
+    lib.hostsim_fmod_2pi_mismatches.argtypes = [C.c_float, C.c_float, C.POINTER(C.c_float)]
+    bad = C.c_float(0)
+    for lo, hi in ((1.0, 1024.0), (1e-30, 1e-29), (4000.0, 4200.0), (0.001, 0.002)):
+        assert lib.hostsim_fmod_2pi_mismatches(lo, hi, C.byref(bad)) == 0, bad.value

@@ -66,7 +66,23 @@ def is_current(lib_path=LIB):
 
 
 def build(force=False, verbose=False):
+    """Build under an exclusive file lock: the ranks of a torchrun launch all call ffi.load() at the same time, and if
+    the shipped library is stale they must not compile and link into the same files concurrently (one builds, the
+    others wait and then find a current library)."""
+    import fcntl
+
     os.makedirs(OBJ, exist_ok=True)
+    with open(os.path.join(OBJ, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():
+                return LIB
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     want = source_hash()
 
     def compile_one(src):
@@ -90,10 +106,12 @@ def build(force=False, verbose=False):
         for _, log, _ in results:
             sys.stderr.write(log)
     if force or any(c for _, _, c in results) or embedded_hash() != want:
-        cmd = [_nvcc(), "-shared", "-o", LIB] + objs
+        tmp = f"{LIB}.tmp.{os.getpid()}"
+        cmd = [_nvcc(), "-shared", "-o", tmp] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(tmp, LIB)  # atomic: a concurrent dlopen sees the old or the new library, never a partial one
     if embedded_hash() != want:
         raise RuntimeError("built library does not carry the hash of its sources")
     return LIB

@@ -92,7 +92,7 @@ inline void build_node(const std::vector<float4> &sph, std::vector<int> &idx, in
 // sph_m: (cx, cy, cz, r). Returns false when no BVH should be used (few spheres, non-finite data).
 inline bool build_bvh(const std::vector<float4> &sph_m, Bvh &out) {
     const int n = (int)sph_m.size();
-    if (n < RR_BVH_MIN_SPHERES || n >= (1 << 27)) return false;
+    if (n < RR_BVH_MIN_SPHERES || n >= (1 << 24)) return false;  // (inner references are byte offsets in an int)
     float rmin = INFINITY;
     for (const float4 &s : sph_m) {
         if (!std::isfinite(s.x) || !std::isfinite(s.y) || !std::isfinite(s.z) || !std::isfinite(s.w)) return false;
@@ -117,14 +117,16 @@ inline bool build_bvh(const std::vector<float4> &sph_m, Bvh &out) {
     for (int i = 0; i < nn; ++i) if (as_int(out.b[i].w) < 0) inner_id[i] = n_inner++;
     if (n_inner == 0) return false;  // a single leaf: the brute-force scan is the better kernel
     out.w.resize((size_t)4 * n_inner);
-    auto ref = [&](int node) { return inner_id[node] >= 0 ? inner_id[node] : ~as_int(out.b[node].w); };
+    // inner reference = BYTE offset of the 64-byte record (the traversal adds it to the array base), leaf = ~code
+    auto ref = [&](int node) { return inner_id[node] >= 0 ? 64 * inner_id[node] : ~as_int(out.b[node].w); };
     for (int i = 0; i < nn; ++i) {
         if (inner_id[i] < 0) continue;
         const int l = i + 1, r = as_int(out.a[l].w);
         float4 *q = &out.w[(size_t)4 * inner_id[i]];
-        q[0] = make_float4(out.a[l].x, out.a[l].y, out.a[l].z, out.b[l].x);
-        q[1] = make_float4(out.b[l].y, out.b[l].z, out.a[r].x, out.a[r].y);
-        q[2] = make_float4(out.a[r].z, out.b[r].x, out.b[r].y, out.b[r].z);
+        // (lo, hi) of one axis side by side: both slab distances of an axis are one packed fma (rr_trace.cuh)
+        q[0] = make_float4(out.a[l].x, out.b[l].x, out.a[l].y, out.b[l].y);
+        q[1] = make_float4(out.a[l].z, out.b[l].z, out.a[r].x, out.b[r].x);
+        q[2] = make_float4(out.a[r].y, out.b[r].y, out.a[r].z, out.b[r].z);
         q[3] = make_float4(as_float(ref(l)), as_float(ref(r)), 0.0f, 0.0f);
     }
     // depth of the tree bounds the traversal stack (one pushed sibling per level)

@@ -61,6 +61,19 @@ struct Lane {
     uint32_t gen = 0;       // ticket generation
 };
 
+// Primary-ray tables (rr_device.cuh, primary_dir_tab) depend on resolution, fov and camera rotation only. A handle keeps
+// the tables of the last RR_PTABS distinct cameras: a launch whose camera is cached binds the table and launches nothing
+// extra (a still camera, every chunk of a chunked frame, every band of a multi-GPU frame); a new camera takes the
+// oldest slot and queues the 6 000-thread fill kernel in front of the render kernel on the same stream. A slot is
+// rewritten RR_PTABS camera changes after it was bound, the same bound on overlapping launches as RR_SLOTS.
+constexpr int RR_PTABS = 32;
+struct PrimTable {
+    float4 *d = nullptr;
+    size_t cap = 0;  // entries
+    int xres = -1, yres = -1;
+    float key[6] = {};  // xfov, yfov, cam_rot[4], compared bitwise
+};
+
 struct rr_scene {
     int device = 0;
     rr::DevScene G{};
@@ -74,6 +87,9 @@ struct rr_scene {
     rr::Counters *d_cnt = nullptr;
     unsigned *d_work = nullptr;  // RR_SLOTS x (work, done, -, -): per-launch tile queue word + block counter
     std::atomic<unsigned> launch_seq{0};
+    std::mutex ptab_mu;
+    PrimTable ptabs[RR_PTABS];
+    unsigned ptab_next = 0;
     float last_ms = 0.0f;
     bool timed = false;
     bool culling = true;
@@ -136,8 +152,38 @@ rr::FrameParams to_dev(const rr_frame_params *p, const rr_scene *s) {
     return d;
 }
 
-int launch(rr_scene *s, const rr::FrameParams &P, void *d_out, size_t row_stride, bool f32, rr::Counters *d_cnt,
+// Binds P.ptab to the cached primary-ray table of this camera, filling a slot first (on `st`) when the camera is new.
+int bind_prim_table(rr_scene *s, rr::FrameParams &P, cudaStream_t st) {
+    P.ptab = nullptr;
+    if (P.xres <= 0 || P.yres <= 0) return RR_OK;
+    float key[6] = {P.xfov, P.yfov, P.cam_rot[0], P.cam_rot[1], P.cam_rot[2], P.cam_rot[3]};
+    std::lock_guard<std::mutex> lk(s->ptab_mu);
+    for (PrimTable &t : s->ptabs)
+        if (t.d && t.xres == P.xres && t.yres == P.yres && memcmp(t.key, key, sizeof key) == 0) { P.ptab = t.d; return RR_OK; }
+    PrimTable &t = s->ptabs[s->ptab_next++ % RR_PTABS];
+    const size_t need = (size_t)P.xres + (size_t)P.yres;
+    if (t.cap < need) {
+        if (t.d) CU(cudaFree(t.d));  // (synchronises the device: nothing still reads the old table)
+        t.d = nullptr; t.cap = 0; t.xres = -1;
+        CU(cudaMalloc(&t.d, need * sizeof(float4)));
+        t.cap = need;
+    }
+    t.xres = -1;  // not valid until the fill kernel is queued
+    cudaError_t e = rr::launch_prim_table(P, t.d, st);
+    if (e != cudaSuccess) return fail_cuda(e, "primary-ray table kernel");
+    t.xres = P.xres; t.yres = P.yres;
+    memcpy(t.key, key, sizeof key);
+    P.ptab = t.d;
+    return RR_OK;
+}
+
+int launch(rr_scene *s, const rr::FrameParams &P_in, void *d_out, size_t row_stride, bool f32, rr::Counters *d_cnt,
            cudaStream_t st, unsigned *d_flag = nullptr, unsigned epoch = 0) {
+    rr::FrameParams P = P_in;
+    if (!P.use_raymarching) {
+        const int rc = bind_prim_table(s, P, st);
+        if (rc != RR_OK) return rc;
+    }
     // Each launch takes the next of RR_SLOTS (work, done) word pairs: the kernels' tile queue and block counter reset
     // themselves in the block that finishes last, so no memset is queued on the stream, and kernels of one handle running
     // concurrently on different streams (ray-trace AND ray-march mode) never share a queue unless more than RR_SLOTS of
@@ -301,6 +347,7 @@ int rr_scene_destroy(rr_scene *s) {
         if (l.copy_stream) cudaStreamSynchronize(l.copy_stream);
     }
     for (void *p : s->allocs) cudaFree(p);
+    for (PrimTable &t : s->ptabs) if (t.d) cudaFree(t.d);
     for (Lane &l : s->lanes) {
         if (l.d_out) cudaFree(l.d_out);
         if (l.ev0) cudaEventDestroy(l.ev0);

@@ -22,6 +22,8 @@ cudaError_t launch_trace(const DevScene &G, const SceneHead &H, const FrameParam
 // launch; the last block resets them), sig.flag: optional completion word, as for the trace kernel.
 cudaError_t launch_march(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
                          Counters *d_cnt, const Signal &sig, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh = true);
+// Fills the primary-ray tables of a frame (FrameParams::ptab layout: xres column entries, then yres row entries).
+cudaError_t launch_prim_table(const FrameParams &P, float4 *d_tab, cudaStream_t stream);
 // Row-band un-interleave (multi-GPU gather epilogue).
 cudaError_t launch_bands_unpack(const FrameParams &P, const void *d_packed, size_t shard_stride, void *d_frame,
                                 cudaStream_t stream);

@@ -18,6 +18,12 @@ constexpr int TRACE_THREADS = RR_TRACE_THREADS;
 #ifndef RR_TRACE_MIN_BLOCKS
 #define RR_TRACE_MIN_BLOCKS 4
 #endif
+// BVH instances run ONE block of 1 024 threads per SM: the staged tree (37 KB for 1 024 spheres) and the per-thread
+// traversal stacks (8 bytes x RR_BVH_SMEM_STACK per thread) then exist once per SM, which leaves room for all 32 resident
+// warps the 64-register budget allows. With 256-thread blocks the same shared memory is needed per block and only three
+// fit (ncu, profiles/r2e_trace_synthetic1024_4k.md: 37 % warps active instead of 50 %).
+__host__ __device__ constexpr int trace_threads(bool bvh) { return bvh ? RR_TRACE_THREADS_BVH : TRACE_THREADS; }
+__host__ __device__ constexpr int trace_min_blocks(bool bvh) { return bvh ? (RR_TRACE_MIN_BLOCKS * TRACE_THREADS) / RR_TRACE_THREADS_BVH : RR_TRACE_MIN_BLOCKS; }
 
 template <typename T>
 __device__ __forceinline__ void copy_list(T *dst, const T *src, int n) {
@@ -36,7 +42,9 @@ __device__ __forceinline__ SceneView stage_scene(const DevScene &G, float4 *smem
     // BVH instances: the first float4s of the dynamic shared memory are the per-thread traversal stacks (trace_smem_bytes)
     S.stk = reinterpret_cast<uint2 *>(smem);
     S.stk_stride = (int)blockDim.x;
-    if (BVH) smem += (RR_BVH_SMEM_STACK * TRACE_THREADS * sizeof(uint2)) / sizeof(float4);
+    S.stk_s = (unsigned)__cvta_generic_to_shared(smem);
+    S.bvh_w_s = 0u; S.bsph_s = 0u;
+    if (BVH) smem += (RR_BVH_SMEM_STACK * trace_threads(true) * sizeof(uint2)) / sizeof(float4);
     if (!stage) return S;
     const int tf = max(G.n_floors - RR_HEAD_FLOORS, 0);
     const int ts = BVH ? 0 : max(G.n_spheres - RR_HEAD_SPHERES, 0);
@@ -71,12 +79,16 @@ __device__ __forceinline__ SceneView stage_scene(const DevScene &G, float4 *smem
     // tail views are indexed with the global list index
     S.sph = sph - RR_HEAD_SPHERES; S.sph_oi = sph_oi - RR_HEAD_SPHERES;
     S.flo_o = flo_o - RR_HEAD_FLOORS; S.flo_n = flo_n - RR_HEAD_FLOORS; S.flo_oi = flo_oi - RR_HEAD_FLOORS;
-    if (BVH) { S.bvh_a = bvh_a; S.bvh_b = bvh_b; S.bvh_w = bvh_a; S.bsph = bsph; S.bsph_oi = bsph_oi; }
+    if (BVH) {
+        S.bvh_a = bvh_a; S.bvh_b = bvh_b; S.bvh_w = bvh_a; S.bsph = bsph; S.bsph_oi = bsph_oi;
+        S.bvh_w_s = (unsigned)__cvta_generic_to_shared(bvh_a);
+        S.bsph_s = (unsigned)__cvta_generic_to_shared(bsph);
+    }
     return S;
 }
 
 template <bool COUNT, bool F32OUT, bool STAGE, bool BVH, int TW, bool HEADONLY>
-__global__ void __launch_bounds__(TRACE_THREADS, RR_TRACE_MIN_BLOCKS)
+__global__ void __launch_bounds__(trace_threads(BVH), trace_min_blocks(BVH))
 trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHead H, const __grid_constant__ FrameParams P,
              void *__restrict__ out, size_t row_stride, Counters *gcnt, int fast_store, float inv_tiles_x, const Signal sig) {
     extern __shared__ float4 rr_smem[];
@@ -138,11 +150,11 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
                 const int ly = ly0;
                 const int irow = local_to_image_row(P, ly);
                 const int orow = P.placed ? irow : ly;
-                const float ez = prim_ez(P, irow);  // one row: the same for the four sub-tiles
+                const float4 prow = __ldg(&P.ptab[P.xres + irow]);  // one row: the same for the four sub-tiles
                 unsigned *wb = reinterpret_cast<unsigned *>(rr_wbuf[threadIdx.x >> 5]);
 #pragma unroll 1
                 for (int sub = 0; sub < SUB; ++sub) {
-                    const V3 c = trace_pixel<COUNT, BVH, HEADONLY>(G, H, S, P, prim_ey(P, x0 + sub * 32 + lane), ez, cnt);
+                    const V3 c = trace_pixel<COUNT, BVH, HEADONLY, BVH && STAGE && RR_BVH_ORDERED>(G, H, S, P, primary_dir_tab(P, __ldg(&P.ptab[x0 + sub * 32 + lane]), prow), cnt);
                     const unsigned rgb = quantize(c.x) | (quantize(c.y) << 8) | (quantize(c.z) << 16);
                     // word w of the 96-byte sub-run holds bytes 4w..4w+3 = pixels pa (and pa+1); lanes 0..23 own one word
                     const int pa = (4 * lane) / 3;
@@ -160,7 +172,7 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
             const int ix = x0 + col, ly = ly0 + row;
             const bool valid = ix < W && ly < rows;
             V3 c = mk(0.0f, 0.0f, 0.0f);
-            if (valid) c = trace_pixel<COUNT, BVH, HEADONLY>(G, H, S, P, ix, local_to_image_row(P, ly), cnt);
+            if (valid) c = trace_pixel<COUNT, BVH, HEADONLY, BVH && STAGE && RR_BVH_ORDERED>(G, H, S, P, ix, local_to_image_row(P, ly), cnt);
             if (F32OUT) {
                 if (valid) {
                     float *o = reinterpret_cast<float *>(out) + ((size_t)(P.placed ? local_to_image_row(P, ly) : ly) * W + ix) * 3;
@@ -178,7 +190,7 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
     finish_launch(sig);
 }
 
-static size_t trace_stack_bytes(bool bvh) { return bvh ? (size_t)RR_BVH_SMEM_STACK * TRACE_THREADS * sizeof(uint2) : 0; }
+static size_t trace_stack_bytes(bool bvh) { return bvh ? (size_t)RR_BVH_SMEM_STACK * trace_threads(true) * sizeof(uint2) : 0; }
 static size_t trace_smem_bytes(const DevScene &G, bool bvh) {
     const size_t tf = G.n_floors > RR_HEAD_FLOORS ? G.n_floors - RR_HEAD_FLOORS : 0;
     size_t b = tf * (2 * sizeof(float4) + sizeof(int)) + 16;
@@ -193,24 +205,25 @@ static cudaError_t launch_hd(const DevScene &G, const SceneHead &H, const FrameP
                              Counters *d_cnt, cudaStream_t stream, const LaunchInfo &li, size_t smem, const Signal &sig) {
     auto kern = trace_kernel<COUNT, F32OUT, STAGE, BVH, TW, HEADONLY>;
     constexpr int TH = TW == 128 ? 1 : 32 / TW;
+    constexpr int THREADS = trace_threads(BVH);
     cudaError_t e;
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TRACE_THREADS, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const int tiles_x = (P.xres + TW - 1) / TW;
     const long long tiles = (long long)tiles_x * ((P.local_rows + TH - 1) / TH);
-    const long long need = (tiles + (TRACE_THREADS / 32) - 1) / (TRACE_THREADS / 32);
+    const long long need = (tiles + (THREADS / 32) - 1) / (THREADS / 32);
     long long grid = (long long)li.sm_count * per_sm;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     const int fast = (!F32OUT && (P.xres % TW == 0) && (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0)) ? 1 : 0;
     const float inv_tx = tiles < (1 << 24) ? 1.0f / (float)tiles_x : 0.0f;
-    kern<<<(unsigned)grid, TRACE_THREADS, smem, stream>>>(G, H, P, d_out, row_stride, d_cnt, fast, inv_tx, sig);
+    kern<<<(unsigned)grid, THREADS, smem, stream>>>(G, H, P, d_out, row_stride, d_cnt, fast, inv_tx, sig);
     return cudaGetLastError();
 }
 
@@ -259,7 +272,9 @@ static cudaError_t launch_two(const DevScene &G, const SceneHead &H, const Frame
 #ifndef RR_BVH_STAGE
 #define RR_BVH_STAGE 1
 #endif
-    const bool stage = (RR_BVH_STAGE || !bvh) && smem + trace_stack_bytes(bvh) <= li.smem_optin / 2;  // keep >= 2 blocks per SM resident
+    // keep >= 2 blocks per SM resident (a BVH instance with 1 024-thread blocks fills the SM with one)
+    const size_t stage_limit = bvh && trace_min_blocks(true) == 1 ? li.smem_optin - 1024 : li.smem_optin / 2;
+    const bool stage = (RR_BVH_STAGE || !bvh) && smem + trace_stack_bytes(bvh) <= stage_limit;
     if (!stage) smem = 0;
     smem += trace_stack_bytes(bvh);  // the traversal stacks are always there
     if (bvh) return stage ? launch_one<COUNT, F32OUT, true, true>(G, H, P, d_out, row_stride, d_cnt, stream, li, smem, sig)

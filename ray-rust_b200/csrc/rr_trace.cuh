@@ -16,6 +16,13 @@
 #pragma once
 #include "rr_device.cuh"
 
+// tools/simt_model.cpp counts traversal steps per ray through these hooks (CPU build only); empty everywhere else
+#ifndef RR_MODEL_RAY
+#define RR_MODEL_RAY()
+#define RR_MODEL_INNER()
+#define RR_MODEL_LEAF(n)
+#endif
+
 namespace rr {
 
 // pointers to the tails of the intersection lists (shared memory when staged)
@@ -34,6 +41,7 @@ struct SceneView {
     // (entry e of thread t at stk[e * stk_stride + t]: conflict-free), deeper entries in local memory. nullptr: all local.
     uint2 *stk;
     int stk_stride;
+    unsigned stk_s, bvh_w_s, bsph_s;  // shared-window addresses of stk / bvh_w / bsph when they are staged (SMEMBVH instances)
 };
 
 struct Hit {
@@ -233,6 +241,42 @@ __device__ __forceinline__ float cull_sqrt_up(float x) {  // >= sqrt(x) for fini
 #endif
 }
 
+// Node / leaf / stack accessors of the ordered traversal. SMEM: the tree and the hot part of the stack are in shared
+// memory and are addressed with 32-bit shared-window addresses (LDS/STS with immediate offsets: one address add per node
+// instead of a 64-bit multiply-add, and no generic-address resolution). Otherwise generic loads through L1.
+struct NodeW { float4 n0, n1, n2; int l, r; };
+template <bool SMEM>
+__device__ __forceinline__ NodeW load_node(const SceneView &S, int cur /* byte offset of the 64-byte record */) {
+    NodeW w;
+#ifndef RR_HOSTSIM
+    if constexpr (SMEM) {
+        const unsigned a = S.bvh_w_s + (unsigned)cur;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.n0.x), "=f"(w.n0.y), "=f"(w.n0.z), "=f"(w.n0.w) : "r"(a));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(w.n1.x), "=f"(w.n1.y), "=f"(w.n1.z), "=f"(w.n1.w) : "r"(a));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+32];" : "=f"(w.n2.x), "=f"(w.n2.y), "=f"(w.n2.z), "=f"(w.n2.w) : "r"(a));
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2+48];" : "=r"(w.l), "=r"(w.r) : "r"(a));
+        return w;
+    }
+#endif
+    const float4 *q = reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(S.bvh_w) + cur);
+    w.n0 = q[0]; w.n1 = q[1]; w.n2 = q[2];
+    const float4 n3 = q[3];
+    w.l = __float_as_int(n3.x); w.r = __float_as_int(n3.y);
+    return w;
+}
+template <bool SMEM>
+__device__ __forceinline__ float4 load_leaf_sphere(const SceneView &S, int k) {
+#ifndef RR_HOSTSIM
+    if constexpr (SMEM) {
+        float4 c;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "r"(S.bsph_s + 16u * (unsigned)k));
+        return c;
+    }
+#endif
+    return S.bsph[k];
+}
+
+template <bool SMEM>
 __device__ __forceinline__ void bvh_scan_ordered(const DevScene &G, const SceneView &S, const V3 &vi, const V3 &eye, int ig,
                                                  bool near_ok, bool far_ok, float &t, int &idx) {
     const float Dx = fmaxf(fabsf(vi.x - G.scene_lo[0]), fabsf(vi.x - G.scene_hi[0]));
@@ -248,56 +292,84 @@ __device__ __forceinline__ void bvh_scan_ordered(const DevScene &G, const SceneV
     const float ez = fabsf(eye.z) < 1e-30f ? copysignf(1e-30f, eye.z) : eye.z;
     // 1/d to 2^-22: a relative error of t, i.e. <= 2.4e-7 D in position, inside the 1e-6 D term of e
     const float ix = cull_rcp(ex), iy = cull_rcp(ey), iz = cull_rcp(ez);
-    // lo planes are moved out by -e, hi planes by +e: (lo - e - o) * i = lo * i - (o + e) * i
-    const float cx_lo = (vi.x + e) * ix, cy_lo = (vi.y + e) * iy, cz_lo = (vi.z + e) * iz;
-    const float cx_hi = (vi.x - e) * ix, cy_hi = (vi.y - e) * iy, cz_hi = (vi.z - e) * iz;
+    // lo planes are moved out by -e, hi planes by +e: (lo - e - o) * i = lo * i - (o + e) * i. The (lo, hi) planes of one
+    // axis sit side by side in the node record, so both slab distances of an axis are ONE packed fma (FFMA2) against the
+    // pair (-(o + e) i, -(o - e) i); 1/d is broadcast to both halves.
+    const F2 kx = f2(-((vi.x + e) * ix), -((vi.x - e) * ix));
+    const F2 ky = f2(-((vi.y + e) * iy), -((vi.y - e) * iy));
+    const F2 kz = f2(-((vi.z + e) * iz), -((vi.z - e) * iz));
+    const F2 bx = f2b(ix), by = f2b(iy), bz = f2b(iz);
+    auto box = [&](const F2 &px, const F2 &py, const F2 &pz) {
+        const F2 tx = fma2(px, bx, kx), ty = fma2(py, by, ky), tz = fma2(pz, bz, kz);
+        const float t1x = f2lo(tx), t2x = f2hi(tx), t1y = f2lo(ty), t2y = f2hi(ty), t1z = f2lo(tz), t2z = f2hi(tz);
+        BoxT r;
+        r.lo = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fmaxf(fminf(t1z, t2z), 0.0f));
+        r.hi = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fminf(fmaxf(t1z, t2z), t));
+        return r;
+    };
     constexpr int DONE = 0x7fffffff;
     // Stack of postponed (farther) children with their entry distances. Its hot part is in shared memory: as two local
     // arrays it was the largest source of local-memory traffic of the BVH instance (profiles/r1_s2_trace_synthetic1024_4k.md:
     // 14 M local loads + 14 M local stores per 4K frame, 65 % L1 hit rate, 2.17x the framebuffer bytes in DRAM traffic).
+    // Entry e of thread t sits at stk + 8 * (e * RR_BVH_BLOCK + t) (conflict-free); `sp` is that byte offset, so with a
+    // power-of-two block the level is sp >> log2(8 * RR_BVH_BLOCK) and "fits in shared memory" is one compare with a
+    // constant. Entry 0 holds a sentinel (DONE, -inf): popping it ends the traversal, so pop() has no empty-stack test.
     constexpr int SD = RR_BVH_SMEM_STACK;
-    int ovf_ref[RR_BVH_STACK - SD];
-    float ovf_t[RR_BVH_STACK - SD];
+    int ovf_ref[RR_BVH_STACK + 1 - SD];
+    float ovf_t[RR_BVH_STACK + 1 - SD];
 #ifdef RR_HOSTSIM
     uint2 hs_stk[SD];
-    uint2 *const stk = hs_stk;
-    const int sst = 1;
+    constexpr unsigned step = 8u;
+    unsigned sp = 0;
 #else
-    uint2 *const stk = S.stk + threadIdx.x;
-    const int sst = S.stk_stride;
+    constexpr unsigned step = 8u * (unsigned)RR_BVH_BLOCK;
+    static_assert((RR_BVH_BLOCK & (RR_BVH_BLOCK - 1)) == 0, "block size of the BVH instances must be a power of two");
+    unsigned sp = 8u * threadIdx.x;
 #endif
-    int sp = 0, cur = 0;
+    constexpr unsigned lim = (unsigned)SD * step;
+    int cur = 0;
     auto push = [&](int ref, float tm) {
-        if (sp < SD) stk[sp * sst] = make_uint2((unsigned)ref, (unsigned)__float_as_int(tm));
-        else { ovf_ref[sp - SD] = ref; ovf_t[sp - SD] = tm; }
-        sp += 1;
+        if (sp < lim) {
+#ifdef RR_HOSTSIM
+            hs_stk[sp / step] = make_uint2((unsigned)ref, (unsigned)__float_as_int(tm));
+#else
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(S.stk_s + sp), "r"(ref), "f"(tm) : "memory");
+#endif
+        } else {
+            ovf_ref[(sp - lim) / step] = ref; ovf_t[(sp - lim) / step] = tm;
+        }
+        sp += step;
     };
     // pop the next stacked subtree that can still hold a winner (entered at or before the current best hit)
     auto pop = [&]() {
         float tm;
         do {
-            if (sp == 0) { cur = DONE; return; }
-            sp -= 1;
-            if (sp < SD) {
-                const uint2 e = stk[sp * sst];
-                cur = (int)e.x;
-                tm = __int_as_float((int)e.y);
+            sp -= step;
+            if (sp < lim) {
+#ifdef RR_HOSTSIM
+                const uint2 en = hs_stk[sp / step];
+                cur = (int)en.x;
+                tm = __int_as_float((int)en.y);
+#else
+                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(cur), "=f"(tm) : "r"(S.stk_s + sp) : "memory");
+#endif
             } else {
-                cur = ovf_ref[sp - SD];
-                tm = ovf_t[sp - SD];
+                cur = ovf_ref[(sp - lim) / step];
+                tm = ovf_t[(sp - lim) / step];
             }
         } while (tm > t);  // NaN: visit
     };
+    push(DONE, -RR_INF);  // sentinel
     while (cur != DONE) {
         // inner nodes until this lane holds a leaf (the warp leaves the loop when every lane does: leaf tests then
         // run with more lanes active than in an if/else per step)
         while ((unsigned)cur < (unsigned)DONE) {
-            // (generic loads on purpose: explicit ld.shared was measured slower, 2.13 vs 2.05 ms on config 4)
-            const float4 n0 = S.bvh_w[4 * cur], n1 = S.bvh_w[4 * cur + 1], n2 = S.bvh_w[4 * cur + 2], n3 = S.bvh_w[4 * cur + 3];
-            const BoxT L = slab_pair(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ix, iy, iz, cx_lo, cy_lo, cz_lo, cx_hi, cy_hi, cz_hi, t);
-            const BoxT R = slab_pair(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ix, iy, iz, cx_lo, cy_lo, cz_lo, cx_hi, cy_hi, cz_hi, t);
+            RR_MODEL_INNER();
+            const NodeW w = load_node<SMEM>(S, cur);
+            const BoxT L = box(f2(w.n0.x, w.n0.y), f2(w.n0.z, w.n0.w), f2(w.n1.x, w.n1.y));
+            const BoxT R = box(f2(w.n1.z, w.n1.w), f2(w.n2.x, w.n2.y), f2(w.n2.z, w.n2.w));
             const bool rej_l = L.hi < L.lo, rej_r = R.hi < R.lo;
-            const int l = __float_as_int(n3.x), r = __float_as_int(n3.y);
+            const int l = w.l, r = w.r;
             if (!rej_l && !rej_r) {
                 const bool left_first = L.lo <= R.lo;
                 push(left_first ? r : l, left_first ? R.lo : L.lo);
@@ -313,8 +385,9 @@ __device__ __forceinline__ void bvh_scan_ordered(const DevScene &G, const SceneV
         if (cur != DONE) {
             const int leaf = ~cur;
             const int first = leaf >> 3, count = leaf & 7;
+            RR_MODEL_LEAF(count);
             for (int k = 0; k < count; ++k)
-                sphere_test(S.bsph[first + k], [&] { return S.bsph_oi[first + k]; }, vi, eye, ig, near_ok, far_ok, t, idx);
+                sphere_test(load_leaf_sphere<SMEM>(S, first + k), [&] { return S.bsph_oi[first + k]; }, vi, eye, ig, near_ok, far_ok, t, idx);
             pop();
         }
     }
@@ -324,11 +397,12 @@ __device__ __forceinline__ void bvh_scan_ordered(const DevScene &G, const SceneV
 // HEADONLY: the whole scene is in the SceneHead (<= RR_HEAD_FLOORS floors, <= RR_HEAD_SPHERES spheres; unused slots hold
 // never-hit objects, fill_head_pairs): no count checks, no tail loops. PRIMARY: the ray starts at the camera (ig = -1,
 // flags = 0) and the origin-dependent terms come from the frame constants.
-template <bool BVH, bool HEADONLY, bool PRIMARY>
+template <bool BVH, bool HEADONLY, bool PRIMARY, bool SMEMBVH = false>
 __device__ __forceinline__ Hit raycast(const DevScene &G, const SceneHead &H, const SceneView &S, const FrameParams &P, const V3 &vi,
                                        const V3 &eye, int ig, unsigned flags) {
     float t = RR_INF;
     int idx = 0;
+    RR_MODEL_RAY();
 #pragma unroll
     for (int f = 0; f < RR_HEAD_FLOORS; ++f) {
         if (HEADONLY || f < S.n_floors) {
@@ -357,7 +431,7 @@ __device__ __forceinline__ Hit raycast(const DevScene &G, const SceneHead &H, co
         const float e2 = dot(eye, eye);
         if (fabsf(e2 - 1.0f) <= 4e-6f) {
 #if RR_BVH_ORDERED
-            bvh_scan_ordered(G, S, vi, eye, ig, near_ok, far_ok, t, idx);
+            bvh_scan_ordered<SMEMBVH>(G, S, vi, eye, ig, near_ok, far_ok, t, idx);
 #else
             bvh_scan(G, S, vi, eye, ig, near_ok, far_ok, t, idx);
 #endif
@@ -438,13 +512,13 @@ constexpr int RR_MAX_STACK = 32;  // >= max_refractions (checked on the host)
 // One pixel. The loop is rotated: its body is "consume the hit of the last scan, set up the next ray, scan", and the
 // first scan (the primary ray, whose origin-dependent terms are frame constants) is peeled off in front of it. There is
 // still ONE general scan site, shared by trace rays and shadow rays of lanes in different phases.
-template <bool COUNT, bool BVH, bool HEADONLY = false>
+template <bool COUNT, bool BVH, bool HEADONLY = false, bool SMEMBVH = false>
 __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneHead &H, const SceneView &S, const FrameParams &P,
-                                          float ey, float ez, Counters &cnt) {
+                                          const V3 &eye0 /* primary direction, render.rs:808-815 */, Counters &cnt) {
     const V3 light = mk(P.light[0], P.light[1], P.light[2]);
     // current trace ray of the running raytrace() frame
     V3 vi = mk(P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]);
-    V3 eye = primary_dir(P, ey, ez);
+    V3 eye = eye0;
     int lev = 1 /* render.rs:1157, first iteration */, ig = -1, depth = 0;
     unsigned flags = 0;
     V3 ret = mk(0.0f, 0.0f, 0.0f), fcs = mk(1.0f, 1.0f, 1.0f);
@@ -465,7 +539,7 @@ __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneHead &H,
     // than the peeled scan saves (measured: 2.05 -> 2.17 ms on the 1 024-sphere scene); they enter the loop at the scan.
     Hit h{RR_INF, 0};
     bool enter_at_scan = BVH;
-    if (!BVH) h = raycast<BVH, HEADONLY, true>(G, H, S, P, vi, eye, -1, 0u);
+    if (!BVH) h = raycast<BVH, HEADONLY, true, SMEMBVH>(G, H, S, P, vi, eye, -1, 0u);
 
     for (;;) {
         V3 ro = vi, rd = eye;
@@ -616,14 +690,14 @@ __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneHead &H,
         }
         }  // !enter_at_scan
         enter_at_scan = false;
-        h = raycast<BVH, HEADONLY, false>(G, H, S, P, ro, rd, rig, rfl);
+        h = raycast<BVH, HEADONLY, false, SMEMBVH>(G, H, S, P, ro, rd, rig, rfl);
     }
 }
 
-template <bool COUNT, bool BVH, bool HEADONLY = false>
+template <bool COUNT, bool BVH, bool HEADONLY = false, bool SMEMBVH = false>
 __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneHead &H, const SceneView &S, const FrameParams &P,
                                           int ix, int iy, Counters &cnt) {
-    return trace_pixel<COUNT, BVH, HEADONLY>(G, H, S, P, prim_ey(P, ix), prim_ez(P, iy), cnt);
+    return trace_pixel<COUNT, BVH, HEADONLY, SMEMBVH>(G, H, S, P, primary_dir_tab(P, __ldg(&P.ptab[ix]), __ldg(&P.ptab[P.xres + iy])), cnt);
 }
 
 }  // namespace rr

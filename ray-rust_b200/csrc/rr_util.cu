@@ -34,6 +34,22 @@ cudaError_t launch_bands_unpack(const FrameParams &P, const void *d_packed, size
     return cudaGetLastError();
 }
 
+// ---- primary-ray tables of the trace kernel (primary_dir_tab, rr_device.cuh) ---------------------
+// xres column entries then yres row entries; the same f32 products the per-pixel code would form (this file is compiled
+// with -fmad=false like the render kernels).
+__global__ void prim_table_kernel(const __grid_constant__ FrameParams P, float4 *__restrict__ tab) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.xres) tab[i] = prim_col_entry(P, i);
+    else if (i < P.xres + P.yres) tab[i] = prim_row_entry(P, i - P.xres);
+}
+
+cudaError_t launch_prim_table(const FrameParams &P, float4 *d_tab, cudaStream_t stream) {
+    const int n = P.xres + P.yres;
+    if (n <= 0) return cudaSuccess;
+    prim_table_kernel<<<(n + 255) / 256, 256, 0, stream>>>(P, d_tab);
+    return cudaGetLastError();
+}
+
 // ---- completion signal / wait (multi-GPU placed frames) ----------------------------------------
 __global__ void signal_kernel(const Signal sig) {
     // everything earlier on this stream has completed and is visible; publish with system scope

@@ -90,6 +90,7 @@ void flatten(const rr_scene_desc *d, Flat &f) {
                     (int)f.flo_o.size() < RR_HEAD_FLOORS ? (int)f.flo_o.size() : RR_HEAD_FLOORS);
 }
 
+std::vector<float4> g_ptab;  // primary-ray tables of the frame being rendered (what rr_ffi.cu's fill kernel writes)
 FrameParams to_dev(const rr_frame_params *p, const SceneHead &H) {
     FrameParams d{};
     d.xres = p->xres; d.yres = p->yres; d.xfov = p->xfov; d.yfov = p->yfov;
@@ -99,6 +100,10 @@ FrameParams to_dev(const rr_frame_params *p, const SceneHead &H) {
     d.max_reflections = p->max_reflections; d.max_refractions = p->max_refractions; d.bg_kind = p->bg_kind;
     d.band_count = 1; d.band_rows = 1; d.band_index = 0; d.local_rows = p->yres; d.row0 = 0; d.placed = 0;
     finish_frame_params(d, H);
+    g_ptab.clear();
+    for (int ix = 0; ix < d.xres; ++ix) g_ptab.push_back(prim_col_entry(d, ix));
+    for (int iy = 0; iy < d.yres; ++iy) g_ptab.push_back(prim_row_entry(d, iy));
+    d.ptab = g_ptab.data();
     return d;
 }
 }  // namespace

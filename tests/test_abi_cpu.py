@@ -27,6 +27,27 @@ def test_library_exports_every_declared_symbol(rr):
     assert lib.rr_abi_version() == 1
 
 
+def test_integration_sys_block_lists_every_symbol():
+    """INTEGRATION.md's Rust `-sys` block (the binding a maintainer would add) declares every entry point of the header,
+    and its #[repr(C)] structs carry every field of the C structs in the same order."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    rust = sorted(set(re.findall(r"pub fn (rr_[a-z0-9_]+)\(", doc)))
+    assert rust == _header_symbols()
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "rr_ffi.h")).read(), flags=re.S)
+    for st in ["rr_material", "rr_object", "rr_texture", "rr_scene_desc", "rr_frame_params", "rr_ray_counts"]:
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (st, st), hdr, flags=re.S).group(1)
+        c_fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = decl.split(None, 1)[1] if not decl.startswith("const") else decl.split(None, 2)[2]
+            c_fields += [re.sub(r"[\*\s]|\[.*?\]", "", n) for n in names.split(",")]
+        rbody = re.search(r"pub struct %s \{(.*?)\n?\}" % st, doc, flags=re.S).group(1)
+        r_fields = re.findall(r"pub ([a-z0-9_]+):", rbody)
+        assert r_fields == c_fields, st
+
+
 def test_struct_layout_matches_header(rr, tmp_path):
     """Compile a C probe against include/rr_ffi.h and compare sizeof/offsetof with the ctypes mirror."""
     import subprocess

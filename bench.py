@@ -456,6 +456,28 @@ def measure(c, name, steps, warmup, primary):
             frame_check = "identical to the 1-GPU frame" if ok else ("MISMATCH" if st[0] == 0 else "FENCE TIMEOUT")
         barrier(c)
 
+    # ---- N>1: what bounds the device-frame step once the kernels are short: every row rendered elsewhere has to enter
+    # rank 0 over ITS NVLink ports. Raw rate of that, measured here: every other rank copies as many bytes as its shard
+    # holds from local memory into rank 0's frame at the same time (plain cudaMemcpyAsync on peer memory), behind the same
+    # device-side barrier, timed like the step (events, max over ranks).
+    nvlink = None
+    if sharded and primary:
+        my_bytes = my_rows * W * 3
+        off = sum(rr.frame_rows(ren.frame_params(band_rows, r, world)) for r in range(rank)) * W * 3
+
+        def step_copy():
+            if rank != 0:  # rank 0 only receives
+                rr.ffi.check(lib.rr_device_copy(local_rank, C.c_void_p(frame_ptr.value + off), C.c_void_p(packed.data_ptr()), my_bytes, sptr))
+            return 0
+
+        cms, _, _, _ = timed(c, step_copy, 10, 3, False, device_barrier)
+        inbound = frame_bytes - rr.frame_rows(ren.frame_params(band_rows, 0, world)) * W * 3
+        nvlink = {"bound": f"nvlink ingress of rank 0 ({world - 1} peers writing their shards at once, cudaMemcpyAsync)",
+                  "bytes_into_rank0": inbound, "raw_copy_ms": cms, "raw_gbs": inbound / cms / 1e6,
+                  "achieved_gbs": inbound / ms_per_step / 1e6, "frac": cms / ms_per_step,
+                  "note": "the step cannot be shorter than max(raw_copy_ms, ideal_kernel_ms): the kernel's own stores ARE the transfer"}
+        barrier(c)
+
     # ---- e2e: the reference-facing call, frame delivered to page-locked HOST memory ------------
     e2e_steps = max(5, min(steps, 50))
     if not sharded:
@@ -624,6 +646,10 @@ def measure(c, name, steps, warmup, primary):
         res["per_rank_kernel_ms"] = kall
         res["ideal_kernel_ms"] = same_1gpu_ms / world
         res["frame_check"] = frame_check
+        if nvlink:
+            res["nvlink_roofline"] = nvlink
+            res["step_lower_bound_ms"] = max(nvlink["raw_copy_ms"], same_1gpu_ms / world)
+            res["efficiency_vs_bound"] = res["step_lower_bound_ms"] / ms_per_step
         if alt:
             res["alt"] = alt
         lib.rr_device_free(local_rank, frame_ptr)
@@ -773,7 +799,8 @@ def main():
             "cpu_baseline": r.get("cpu_baseline"),
             "wall_s_timed_region": r["_wall_s"],
         }
-        for k in ("e2e_pageable", "same_workload_1gpu_ms", "efficiency_same_workload", "per_rank_kernel_ms", "ideal_kernel_ms", "frame_check", "alt"):
+        for k in ("e2e_pageable", "same_workload_1gpu_ms", "efficiency_same_workload", "per_rank_kernel_ms", "ideal_kernel_ms", "frame_check",
+                  "nvlink_roofline", "step_lower_bound_ms", "efficiency_vs_bound", "alt"):
             if k in r:
                 line[k] = r[k]
         if configs:

@@ -248,6 +248,9 @@ int rr_fence_wait_device(int device, const uint32_t *d_flags, int32_t count, uin
 int rr_fence_signal_device(int device, uint32_t *d_flag, uint32_t epoch, void *cuda_stream);
 int rr_device_memset(int device, void *d_ptr, int value, size_t bytes);
 int rr_device_read(int device, const void *d_ptr, void *host, size_t bytes);
+/* Asynchronous device-to-device copy on `cuda_stream` (NULL = default stream); dst/src may be local or peer (rr_ipc_open)
+ * memory. bench.py measures the raw NVLink ingress rate of the frame owner with it, as the roofline of the multi-GPU step. */
+int rr_device_copy(int device, void *d_dst, const void *d_src, size_t bytes, void *cuda_stream);
 int rr_device_alloc(int device, size_t bytes, void **d_ptr);
 int rr_device_free(int device, void *d_ptr);
 int rr_ipc_export(void *d_ptr, uint8_t handle[64]);

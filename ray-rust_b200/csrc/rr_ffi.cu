@@ -771,6 +771,13 @@ int rr_device_memset(int device, void *d_ptr, int value, size_t bytes) {
     return RR_OK;
 }
 
+int rr_device_copy(int device, void *d_dst, const void *d_src, size_t bytes, void *cuda_stream) {
+    if (!d_dst || !d_src) return fail(RR_ERR_BAD_ARG, "pointer is null");
+    CU(cudaSetDevice(device));
+    CU(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, reinterpret_cast<cudaStream_t>(cuda_stream)));
+    return RR_OK;
+}
+
 int rr_device_read(int device, const void *d_ptr, void *host, size_t bytes) {
     if (!d_ptr || !host) return fail(RR_ERR_BAD_ARG, "d_ptr/host is null");
     CU(cudaSetDevice(device));

@@ -243,7 +243,7 @@ __device__ __forceinline__ bool spheres_far(const SceneHead &H, const V3 &vi, bo
 // floor's index); anything else (a NaN or infinite distance, a failed test, an ignored floor, more floors or
 // spheres than the head holds, inline glow) leaves it without having changed any state and takes the full step.
 template <int GLOW, bool MBVH = false>
-__device__ __forceinline__ MarchResult raymarch_single(const SceneHead &H, const MarchView &S, const V3 &init_pos,
+__device__ __forceinline__ MarchResult raymarch_single(const SceneHead &H, const MarchView &S, const PackK &K, const V3 &init_pos,
                                                        const V3 &eye, int ig, bool track, float glow_bound) {
     int iter = 0;
     float travel = 0.0f;
@@ -258,6 +258,45 @@ __device__ __forceinline__ MarchResult raymarch_single(const SceneHead &H, const
     bool creeping = false;  // the previous step reported all_far; df = floor distance at pos
     float df = 0.0f;
     for (;;) {
+        // Warp-wide creeping: when EVERY lane of the warp that is still in this march creeps (the tiles next to the horizon,
+        // for thousands of iterations), the step runs in a tight inner loop without the full step's code around it, and in
+        // packed arithmetic: the x and y components of every vector operation share one instruction (F2, rr_device.cuh:
+        // the same IEEE operations, unfused, in the same order), as do the two thresholds of the far test. The loop is
+        // left, with nothing committed for the current step, as soon as any lane's step is not a plain creeping step
+        // (failed far test, termination); the general iteration below then handles every lane individually.
+        {
+            const unsigned act = __activemask();
+            if (__all_sync(act, creeping)) {
+                const F2 exy = f2(eye.x, eye.y), foxy = f2(fo.x, fo.y), fnxy = f2(fn.x, fn.y), gxy = f2(H.grp.x, H.grp.y);
+                const F2 rr2 = f2b(H.grp.w), margin = f2(1.00001f, 1.00002f);
+                const bool two = GLOW == 1 && track;  // the glow threshold applies as well
+                F2 pxy = f2(pos.x, pos.y);
+                float pz = pos.z;
+                for (;;) {
+                    // npos = (eye * df) + pos; ndf = max(dot(npos - fo, fn), 0)
+                    const F2 nxy = add2(K, mul2(K, exy, f2b(df)), pxy);
+                    const float nz = eye.z * df + pz;
+                    const F2 qxy = mul2(K, sub2(K, nxy, foxy), fnxy);
+                    const float ndf = fmaxf((f2lo(qxy) + f2hi(qxy)) + (nz - fo.z) * fn.z, 0.0f);
+                    // spheres_far(): d = grp - pos, sq = d.d, sq > (df + R)^2 * 1.00001 [and sq > (gl * ik + R)^2 * 1.00002]
+                    const F2 dxy = sub2(K, gxy, pxy);
+                    const float dz = H.grp.z - pz;
+                    const F2 sxy = mul2(K, dxy, dxy);
+                    const float sq = (f2lo(sxy) + f2hi(sxy)) + dz * dz;
+                    const F2 tt = add2(K, f2(df, min_dist * H.grp_ik), rr2);
+                    const F2 th = mul2(K, mul2(K, tt, tt), margin);
+                    const bool far = (sq > f2lo(th)) & (!two | (sq > f2hi(th)));
+                    const bool ok = (df < RR_INF) & far & !(df < RAYMARCH_EPS) & !(FAR_AWAY < df) & !(MAX_ITER < iter + 1);
+                    if (!__all_sync(act, ok)) break;
+                    travel += df;
+                    iter += 1;
+                    pxy = nxy;
+                    pz = nz;
+                    df = ndf;
+                }
+                pos = mk(f2lo(pxy), f2hi(pxy), pz);
+            }
+        }
         if (creeping) {
             const V3 npos = (eye * df) + pos;                      // speculative: the step if it is a creeping one
             const float ndf = fmaxf(dot(npos - fo, fn), 0.0f);     // ... and the floor distance after it
@@ -309,6 +348,7 @@ template <bool COUNT, int GLOW, bool MBVH = false>
 __device__ __forceinline__ V3 march_pixel(const DevScene &G, const SceneHead &H, const MarchView &S, const FrameParams &P,
                                           int ix, int iy, Counters &cnt) {
     const V3 light = mk(P.light[0], P.light[1], P.light[2]);
+    const PackK K{f2(P.pk_one.x, P.pk_one.y), f2(P.pk_nz.x, P.pk_nz.y), f2(P.pk_neg1.x, P.pk_neg1.y)};
     V3 pos = mk(P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]);
     V3 eye = primary_ray(P, ix, iy);
     int lev = 0, ig = -1, depth = 0;
@@ -333,7 +373,7 @@ __device__ __forceinline__ V3 march_pixel(const DevScene &G, const SceneHead &H,
             ro = pt + (light * F32_EPSILON);  // render.rs:1034
             rd = light; rig = hidx;
         }
-        const MarchResult r = raymarch_single<GLOW, MBVH>(H, S, ro, rd, rig, !shadow_phase, shadow_phase ? RR_INF : mmd);
+        const MarchResult r = raymarch_single<GLOW, MBVH>(H, S, K, ro, rd, rig, !shadow_phase, shadow_phase ? RR_INF : mmd);
         if (COUNT) {
             if (shadow_phase) {
                 cnt.shadow++;

@@ -136,6 +136,7 @@ PROTOTYPES = {
     "rr_fence_signal_device": (C.c_int, [C.c_int, _P, C.c_uint32, _P]),
     "rr_device_memset": (C.c_int, [C.c_int, _P, C.c_int, C.c_size_t]),
     "rr_device_read": (C.c_int, [C.c_int, _P, _P, C.c_size_t]),
+    "rr_device_copy": (C.c_int, [C.c_int, _P, _P, C.c_size_t, _P]),
     "rr_device_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_P)]),
     "rr_device_free": (C.c_int, [C.c_int, _P]),
     "rr_ipc_export": (C.c_int, [_P, _P]),

@@ -45,6 +45,8 @@ static inline unsigned __float2uint_rz(float x) {
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline unsigned __shfl_sync(unsigned, unsigned v, int) { return v; }
+static inline unsigned __activemask() { return 1u; }
+static inline bool __all_sync(unsigned, bool p) { return p; }  // a one-lane warp
 static inline unsigned long long __shfl_down_sync(unsigned, unsigned long long v, int) { return v; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 using std::min;

@@ -104,3 +104,26 @@ def test_chunked_host_pipeline_odd_rows(rr, w, h):
     del pinned
     scene.lib.rr_host_free(host)
     scene.close()
+
+
+def test_many_cameras_one_handle(rr, oracle):
+    """One resident scene rendered from 40 different cameras and then from the first ones again: more cameras than the
+    handle keeps primary-ray tables for (rr_ffi.cu, RR_PTABS = 32), so table slots are evicted and refilled, and a camera
+    whose table is still cached must bind it without a refill. Every frame must be the oracle's."""
+    ren = rr.default_scene(96, 64)
+    scene = rr.DeviceScene(ren, 0)
+    f32 = np.float32
+    order = list(range(40)) + [0, 1, 39, 20, 0]
+    for k in order:
+        pyr = (f32(0.01 * k), -rr.scene.PI / f32(2) + f32(0.003 * k), -rr.scene.PI / f32(2) - f32(0.002 * k))
+        ren.camera = rr.scene.Camera((f32(2.0 * k), f32(-150.0), f32(-300.0 + k)), pyr)
+        got = scene.render_f32(ren.frame_params())
+        ref = oracle.render(ren, threads=NCPU, want_f32=True, want_tags=True)
+        clean = (ref["tags"] & 1) == 0
+        assert np.array_equal(got.view(np.uint32)[clean], ref["f32"].view(np.uint32)[clean]), k
+        if k % 7 == 0:  # resolution / fov changes re-key the tables too
+            small = rr.default_scene(48, 32)
+            small.camera = ren.camera
+            g2 = scene.render_rgb8(small.frame_params())
+            assert np.abs(g2.astype(int) - oracle.render(small, threads=NCPU)["u8"].astype(int)).max() <= 1
+    scene.close()

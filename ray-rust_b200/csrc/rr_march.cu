@@ -48,6 +48,8 @@ __device__ __forceinline__ MarchView stage_march(const DevScene &G, float4 *smem
     return S;
 }
 
+// (no minimum block count on purpose: __launch_bounds__(128, 7) yields the same 72 registers, scheduled differently, and a
+// 7-10 % slower kernel; (128, 8) = 64 registers is 6 % slower too: profiles/r2k_ab_march.txt)
 template <bool COUNT, bool F32OUT, bool STAGE, int GLOW, bool MBVH>
 __global__ void __launch_bounds__(MARCH_THREADS)
 march_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHead H, const __grid_constant__ FrameParams P,

@@ -90,8 +90,7 @@ __device__ __forceinline__ SceneView stage_scene(const DevScene &G, float4 *smem
 template <bool COUNT, bool F32OUT, bool STAGE, bool BVH, int TW, bool HEADONLY>
 __global__ void __launch_bounds__(trace_threads(BVH), trace_min_blocks(BVH))
 trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHead H, const __grid_constant__ FrameParams P,
-             void *__restrict__ out, size_t row_stride, Counters *gcnt, int fast_store, float inv_tiles_x, const Signal sig,
-             int sub_tail) {
+             void *__restrict__ out, size_t row_stride, Counters *gcnt, int fast_store, float inv_tiles_x, const Signal sig) {
     extern __shared__ float4 rr_smem[];
     const SceneView S = stage_scene<BVH>(G, rr_smem, STAGE);
 
@@ -121,27 +120,18 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
     // 4K 1 024 spheres (profiles/r1_s2_tile_schedule.md): 16/16 0.249 / 0.955 / 2.78, 13/16 0.239 / 0.910 / 2.71,
     // 8/16 0.225 / 0.862 / 2.35, 6/16 0.225 / 0.864 / 2.06, 0/16 0.234 / 0.892 / 2.05. Contiguous chunks per warp
     // (guided self-scheduling) lose badly (0.35 / 1.28 / 4.0): neighbouring tiles cost alike.
+    // Tried and dropped in round 2 (profiles/r2i_shard_time.txt, r2h_bench_n8_tail*.json): a smaller static share for small
+    // launches and handing the last macro tiles out as their four 32x1 sub-tiles. Neither changes the time of a 1/8-frame
+    // launch (0.105 ms against 0.082 ideal at 8K: that gap is not the tile schedule), and the 96-byte stores of the sub-tiles
+    // cost the 8-GPU step 5 % of its NVLink store rate.
     constexpr int STATIC_16THS = BVH ? 6 : 8;
     const int n_static = sig.work ? (int)(((long long)ntiles * STATIC_16THS) >> 4) : ntiles;
-    // Macro-tile instances: the LAST `sub_tail` macro tiles of the queue are handed out as their four 32x1 sub-tiles (96-byte
-    // stores). A launch ends one tile-time after the queue runs dry; for a shard of a frame (1/8 of an 8K frame on 8 GPUs,
-    // the row chunks of the host pipeline) a 128-pixel tile-time is 10-15 % of the whole kernel, a 32-pixel one a quarter of that.
-    const int q_macro = (TW == 128) ? max(ntiles - n_static - sub_tail, 0) : (ntiles - n_static);
     int nt = gw;
     for (;;) {
-        int sub0 = 0, nsub = SUB;
         if (sig.work && nt >= n_static) {  // warp-uniform: the static share is done (queue tiles are >= n_static, so it stays done)
-            int q = 0;
-            if (lane == 0) q = (int)atomicAdd(sig.work, 1u);
-            q = __shfl_sync(0xffffffffu, q, 0);
-            if (TW != 128 || q < q_macro) {
-                nt = n_static + q;
-            } else {
-                const int sq = q - q_macro;
-                nt = n_static + q_macro + (sq >> 2);
-                sub0 = sq & 3;
-                nsub = 1;
-            }
+            nt = 0;
+            if (lane == 0) nt = n_static + (int)atomicAdd(sig.work, 1u);
+            nt = __shfl_sync(0xffffffffu, nt, 0);
         }
         if (nt >= ntiles) break;
         const int tile = nt;
@@ -167,7 +157,7 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
                 const float4 prow = __ldg(&P.ptab[P.xres + irow]);  // one row: the same for the four sub-tiles
                 unsigned *wb = reinterpret_cast<unsigned *>(rr_wbuf[threadIdx.x >> 5]);
 #pragma unroll 1
-                for (int sub = sub0; sub < sub0 + nsub; ++sub) {
+                for (int sub = 0; sub < SUB; ++sub) {
                     const V3 c = trace_pixel<COUNT, BVH, HEADONLY, BVH && STAGE && RR_BVH_ORDERED>(G, H, S, P, primary_dir_tab(P, __ldg(&P.ptab[x0 + sub * 32 + lane]), prow), cnt);
                     const unsigned rgb = quantize(c.x) | (quantize(c.y) << 8) | (quantize(c.z) << 16);
                     // word w of the 96-byte sub-run holds bytes 4w..4w+3 = pixels pa (and pa+1); lanes 0..23 own one word
@@ -178,11 +168,9 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
                     if (lane < 24) wb[sub * 24 + lane] = (unsigned)(both >> (8 * ((4 * lane - 3 * pa) & 3)));
                 }
                 __syncwarp();
-                uint8_t *dst = reinterpret_cast<uint8_t *>(out) + (size_t)orow * row_stride + (size_t)x0 * 3;
-                if (lane < 24) {
-                    if (nsub == SUB) *reinterpret_cast<uint4 *>(dst + 16 * lane) = rr_wbuf[threadIdx.x >> 5][lane];
-                    else *reinterpret_cast<unsigned *>(dst + 96 * sub0 + 4 * lane) = wb[sub0 * 24 + lane];
-                }
+                if (lane < 24)
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(out) + (size_t)orow * row_stride + (size_t)x0 * 3 + 16 * lane) =
+                        rr_wbuf[threadIdx.x >> 5][lane];
                 __syncwarp();
             } else {
             const int ix = x0 + col, ly = ly0 + row;
@@ -239,10 +227,7 @@ static cudaError_t launch_hd(const DevScene &G, const SceneHead &H, const FrameP
     if (grid < 1) grid = 1;
     const int fast = (!F32OUT && (P.xres % TW == 0) && (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0)) ? 1 : 0;
     const float inv_tx = tiles < (1 << 24) ? 1.0f / (float)tiles_x : 0.0f;
-    // sub-tile tail of the macro-tile instances: one macro tile per resident warp by default (RR_SUB_TAIL_16THS: x/16 of that)
-    static const int tail16 = [] { const char *e = getenv("RR_SUB_TAIL_16THS"); return e ? atoi(e) : 16; }();
-    const int sub_tail = TW == 128 ? (int)((grid * (THREADS / 32) * (long long)tail16) >> 4) : 0;
-    kern<<<(unsigned)grid, THREADS, smem, stream>>>(G, H, P, d_out, row_stride, d_cnt, fast, inv_tx, sig, sub_tail);
+    kern<<<(unsigned)grid, THREADS, smem, stream>>>(G, H, P, d_out, row_stride, d_cnt, fast, inv_tx, sig);
     return cudaGetLastError();
 }
 

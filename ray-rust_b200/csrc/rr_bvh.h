@@ -96,6 +96,8 @@ inline bool build_bvh(const std::vector<float4> &sph_m, Bvh &out) {
     float rmin = INFINITY;
     for (const float4 &s : sph_m) {
         if (!std::isfinite(s.x) || !std::isfinite(s.y) || !std::isfinite(s.z) || !std::isfinite(s.w)) return false;
+        // (coordinates beyond 5e7: the slab arithmetic of the traversal could overflow, see raycast() in rr_trace.cuh)
+        if (std::fabs(s.x) + std::fabs(s.w) > 5e7f || std::fabs(s.y) + std::fabs(s.w) > 5e7f || std::fabs(s.z) + std::fabs(s.w) > 5e7f) return false;
         rmin = std::fmin(rmin, std::fabs(s.w));
     }
     std::vector<int> idx(n);
@@ -123,10 +125,23 @@ inline bool build_bvh(const std::vector<float4> &sph_m, Bvh &out) {
         if (inner_id[i] < 0) continue;
         const int l = i + 1, r = as_int(out.a[l].w);
         float4 *q = &out.w[(size_t)4 * inner_id[i]];
-        // (lo, hi) of one axis side by side: both slab distances of an axis are one packed fma (rr_trace.cuh)
-        q[0] = make_float4(out.a[l].x, out.b[l].x, out.a[l].y, out.b[l].y);
-        q[1] = make_float4(out.a[l].z, out.b[l].z, out.a[r].x, out.b[r].x);
-        q[2] = make_float4(out.a[r].y, out.b[r].y, out.a[r].z, out.b[r].z);
+        // centre / half extent of both child boxes, (left, right) side by side per component: the traversal forms the slab
+        // distances of both children with one packed fma per term (rr_trace.cuh). h is rounded UP until [c - h, c + h]
+        // contains the box exactly.
+        float c[2][3], h[2][3];
+        const int ch[2] = {l, r};
+        for (int k = 0; k < 2; ++k) {
+            const float lo3[3] = {out.a[ch[k]].x, out.a[ch[k]].y, out.a[ch[k]].z}, hi3[3] = {out.b[ch[k]].x, out.b[ch[k]].y, out.b[ch[k]].z};
+            for (int a = 0; a < 3; ++a) {
+                c[k][a] = (float)(((double)lo3[a] + (double)hi3[a]) * 0.5);
+                h[k][a] = (float)(((double)hi3[a] - (double)lo3[a]) * 0.5);
+                while ((double)c[k][a] - (double)h[k][a] > (double)lo3[a] || (double)c[k][a] + (double)h[k][a] < (double)hi3[a])
+                    h[k][a] = std::nextafter(h[k][a], INFINITY);
+            }
+        }
+        q[0] = make_float4(c[0][0], c[1][0], c[0][1], c[1][1]);
+        q[1] = make_float4(c[0][2], c[1][2], h[0][0], h[1][0]);
+        q[2] = make_float4(h[0][1], h[1][1], h[0][2], h[1][2]);
         q[3] = make_float4(as_float(ref(l)), as_float(ref(r)), 0.0f, 0.0f);
     }
     // depth of the tree bounds the traversal stack (one pushed sibling per level)

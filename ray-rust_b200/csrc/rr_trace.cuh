@@ -202,23 +202,20 @@ __device__ __forceinline__ void bvh_scan(const DevScene &G, const SceneView &S, 
 // are those of bvh_scan(); the visiting order cannot change the result because sphere_test() applies the full
 // (t, original index) comparison. Child reference: >= 0 inner node, < 0 leaf ~((first << 3) | count).
 
-// Slab arithmetic of the ordered traversal: t = plane * (1/d) - (o +- e) * (1/d) as ONE fused multiply-add per plane
-// (cull-only arithmetic, so contraction is allowed). Its rounding differs from (plane - o) * (1/d): the product
-// (o +- e) * (1/d) is rounded on its own, an absolute error of 2^-24 |o| in position space that does not shrink when the
-// plane is close to the origin. It is covered by inflating e by 4e-7 * max|o_k| (3.3x the two roundings involved);
-// the final rounding of t (2^-24 |t d| <= 6e-8 D) and the reciprocal's error stay inside the 1e-6 D term of e.
-// reject <=> min(tmax, t) < max(tmin, 0)   (t >= 0 always; a NaN slab distance is ignored by fminf/fmaxf = no cull).
+// Slab arithmetic of the ordered traversal (cull-only arithmetic, so contraction is allowed). A child box is stored as centre
+// c and half extent h (h rounded up by the builder so that [c - h, c + h] contains the exact box), and per axis
+//   t_near = (c - o) i - (h + e) |i|,   t_far = (c - o) i + (h + e) |i|        (i = 1/d, e = the per-ray inflation)
+// which needs no min/max to sort the two planes: the sign of the direction is in |i|. Each is two fused multiply-adds,
+// fma(h, -+|i|, fma(c, i, k)) with the per-ray constants k_near = -(o i) - e |i|, k_far = -(o i) + e |i|, and the left and the
+// right child of a node share every instruction (FFMA2: the node record holds (c_L, c_R) and (h_L, h_R) side by side).
+// Per node that is 12 FFMA2 + 8 min/max, against 6 FFMA2 + 20 min/max for lo/hi planes: FMNMX runs on the half-rate ALU
+// pipe, which was the busiest unit of the BVH instance (ncu, profiles/r2j_trace_synthetic1024_4k.md: ALU 70 %, math-pipe
+// throttle the top stall).
+// Rounding (position space = t error / |i|): o i and k are rounded on their own (2 x 2^-24 |o|), fma(c, i, k) and the
+// final fma once each (2 x 2^-24 of a distance <= D); e |i| adds 2^-24 e. These are covered by the 4e-7 max|o_k| term of e
+// (3.3x) and, together with the reciprocal's 2.4e-7 D, by its 1e-6 D term (2.7x).
+// reject <=> min(t_far's, t) < max(t_near's, 0)   (t >= 0 always; a NaN slab distance is ignored by fminf/fmaxf = no cull).
 struct BoxT { float lo, hi; };
-__device__ __forceinline__ BoxT slab_pair(float lox, float loy, float loz, float hix, float hiy, float hiz, float ix, float iy, float iz,
-                                          float cx_lo, float cy_lo, float cz_lo, float cx_hi, float cy_hi, float cz_hi, float t) {
-    const float t1x = __fmaf_rn(lox, ix, -cx_lo), t2x = __fmaf_rn(hix, ix, -cx_hi);
-    const float t1y = __fmaf_rn(loy, iy, -cy_lo), t2y = __fmaf_rn(hiy, iy, -cy_hi);
-    const float t1z = __fmaf_rn(loz, iz, -cz_lo), t2z = __fmaf_rn(hiz, iz, -cz_hi);
-    BoxT r;
-    r.lo = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fmaxf(fminf(t1z, t2z), 0.0f));
-    r.hi = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fminf(fmaxf(t1z, t2z), t));
-    return r;
-}
 
 // cull-only helpers: approximate reciprocal / square root (MUFU, ~2^-22 relative error, no IEEE fix-up branches). Their
 // error is inside the margins: every quantity built from them is padded upwards by >= 1e-6 relative below.
@@ -292,21 +289,12 @@ __device__ __forceinline__ void bvh_scan_ordered(const DevScene &G, const SceneV
     const float ez = fabsf(eye.z) < 1e-30f ? copysignf(1e-30f, eye.z) : eye.z;
     // 1/d to 2^-22: a relative error of t, i.e. <= 2.4e-7 D in position, inside the 1e-6 D term of e
     const float ix = cull_rcp(ex), iy = cull_rcp(ey), iz = cull_rcp(ez);
-    // lo planes are moved out by -e, hi planes by +e: (lo - e - o) * i = lo * i - (o + e) * i. The (lo, hi) planes of one
-    // axis sit side by side in the node record, so both slab distances of an axis are ONE packed fma (FFMA2) against the
-    // pair (-(o + e) i, -(o - e) i); 1/d is broadcast to both halves.
-    const F2 kx = f2(-((vi.x + e) * ix), -((vi.x - e) * ix));
-    const F2 ky = f2(-((vi.y + e) * iy), -((vi.y - e) * iy));
-    const F2 kz = f2(-((vi.z + e) * iz), -((vi.z - e) * iz));
+    const float aix = fabsf(ix), aiy = fabsf(iy), aiz = fabsf(iz);
+    const float ox = vi.x * ix, oy = vi.y * iy, oz = vi.z * iz, eix = e * aix, eiy = e * aiy, eiz = e * aiz;
     const F2 bx = f2b(ix), by = f2b(iy), bz = f2b(iz);
-    auto box = [&](const F2 &px, const F2 &py, const F2 &pz) {
-        const F2 tx = fma2(px, bx, kx), ty = fma2(py, by, ky), tz = fma2(pz, bz, kz);
-        const float t1x = f2lo(tx), t2x = f2hi(tx), t1y = f2lo(ty), t2y = f2hi(ty), t1z = f2lo(tz), t2z = f2hi(tz);
-        BoxT r;
-        r.lo = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fmaxf(fminf(t1z, t2z), 0.0f));
-        r.hi = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fminf(fmaxf(t1z, t2z), t));
-        return r;
-    };
+    const F2 nax = f2b(-aix), nay = f2b(-aiy), naz = f2b(-aiz), pax = f2b(aix), pay = f2b(aiy), paz = f2b(aiz);
+    const F2 knx = f2b(-ox - eix), kny = f2b(-oy - eiy), knz = f2b(-oz - eiz);
+    const F2 kfx = f2b(-ox + eix), kfy = f2b(-oy + eiy), kfz = f2b(-oz + eiz);
     constexpr int DONE = 0x7fffffff;
     // Stack of postponed (farther) children with their entry distances. Its hot part is in shared memory: as two local
     // arrays it was the largest source of local-memory traffic of the BVH instance (profiles/r1_s2_trace_synthetic1024_4k.md:
@@ -366,8 +354,17 @@ __device__ __forceinline__ void bvh_scan_ordered(const DevScene &G, const SceneV
         while ((unsigned)cur < (unsigned)DONE) {
             RR_MODEL_INNER();
             const NodeW w = load_node<SMEM>(S, cur);
-            const BoxT L = box(f2(w.n0.x, w.n0.y), f2(w.n0.z, w.n0.w), f2(w.n1.x, w.n1.y));
-            const BoxT R = box(f2(w.n1.z, w.n1.w), f2(w.n2.x, w.n2.y), f2(w.n2.z, w.n2.w));
+            // (left, right) pairs: n0 = (c.x, c.x, c.y, c.y), n1 = (c.z, c.z, h.x, h.x), n2 = (h.y, h.y, h.z, h.z)
+            const F2 cx = f2(w.n0.x, w.n0.y), cy = f2(w.n0.z, w.n0.w), cz = f2(w.n1.x, w.n1.y);
+            const F2 hx = f2(w.n1.z, w.n1.w), hy = f2(w.n2.x, w.n2.y), hz = f2(w.n2.z, w.n2.w);
+            const F2 nx = fma2(hx, nax, fma2(cx, bx, knx)), fx = fma2(hx, pax, fma2(cx, bx, kfx));
+            const F2 ny = fma2(hy, nay, fma2(cy, by, kny)), fy = fma2(hy, pay, fma2(cy, by, kfy));
+            const F2 nz = fma2(hz, naz, fma2(cz, bz, knz)), fz = fma2(hz, paz, fma2(cz, bz, kfz));
+            BoxT L, R;
+            L.lo = fmaxf(fmaxf(f2lo(nx), f2lo(ny)), fmaxf(f2lo(nz), 0.0f));
+            L.hi = fminf(fminf(f2lo(fx), f2lo(fy)), fminf(f2lo(fz), t));
+            R.lo = fmaxf(fmaxf(f2hi(nx), f2hi(ny)), fmaxf(f2hi(nz), 0.0f));
+            R.hi = fminf(fminf(f2hi(fx), f2hi(fy)), fminf(f2hi(fz), t));
             const bool rej_l = L.hi < L.lo, rej_r = R.hi < R.lo;
             const int l = w.l, r = w.r;
             if (!rej_l && !rej_r) {
@@ -428,8 +425,11 @@ __device__ __forceinline__ Hit raycast(const DevScene &G, const SceneHead &H, co
         // off an un-normalised floor normal (face_normal is used as given, render.rs:553-563, appendix A Q22),
         // where eye += n*(-2 eye.n) changes its length. Such rays (and NaN directions) scan every sphere.
         // |eye|^2 = 1 + delta perturbs the discriminant by delta*c <= 4e-6 d^2, inside the margin M (rr_trace.cuh).
+        // Origins beyond 5e7 also scan every sphere (as do scenes with such coordinates: the builder refuses them): with
+        // |1/d| capped at 1e30 (axis-parallel rays) the slab terms (c - o)/d stay below the f32 range, so no infinity can
+        // turn a box the ray is inside of into a reject.
         const float e2 = dot(eye, eye);
-        if (fabsf(e2 - 1.0f) <= 4e-6f) {
+        if (fabsf(e2 - 1.0f) <= 4e-6f && fmaxf(fmaxf(fabsf(vi.x), fabsf(vi.y)), fabsf(vi.z)) < 5e7f) {
 #if RR_BVH_ORDERED
             bvh_scan_ordered<SMEMBVH>(G, S, vi, eye, ig, near_ok, far_ok, t, idx);
 #else

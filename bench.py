@@ -303,9 +303,10 @@ def measure(c, name, steps, warmup, primary):
     scene = rr.DeviceScene(ren, local_rank)
     sharded = c.sharded
     band_rows = c.band_rows
-    p = ren.frame_params(band_rows, rank, world) if sharded else ren.frame_params()
+    p_eq = ren.frame_params(band_rows, rank, world) if sharded else ren.frame_params()  # equal shares (e2e, gather alternative)
+    p = p_eq                                                                            # the device-frame step's shard (may get unequal spans below)
     whole = ren.frame_params()
-    my_rows = rr.frame_rows(p)
+    eq_rows = rr.frame_rows(p_eq)
     max_rows = c.bands.max_shard_rows(H, band_rows, world) if sharded else H
     shard_bytes = max_rows * W * 3
     frame_bytes = H * W * 3
@@ -351,7 +352,7 @@ def measure(c, name, steps, warmup, primary):
                 rr.ffi.check(lib.rr_fence_signal_device(local_rank, go_ptr, gate[0], sptr))
             rr.ffi.check(lib.rr_fence_wait_device(local_rank, go_ptr, 1, gate[0], 5000, status_ptr, sptr))
         tok = torch.zeros(1, dtype=torch.float32, device=dev)
-        packed = torch.empty(shard_bytes, dtype=torch.uint8, device=dev)
+        packed = torch.empty(frame_bytes, dtype=torch.uint8, device=dev)  # a shard in packed order (any share of the frame)
         gathered = torch.empty(world * shard_bytes, dtype=torch.uint8, device=dev) if rank == 0 and primary else None
         gframe = torch.empty(frame_bytes, dtype=torch.uint8, device=dev) if rank == 0 and primary else None
     else:
@@ -366,26 +367,99 @@ def measure(c, name, steps, warmup, primary):
         # fused: the render kernel stores its rows into rank 0's frame over NVLink AND publishes its completion word
         # there; rank 0's stream waits on the words. No collective in the step.
         epoch[0] += 1
-        rr.ffi.check(lib.rr_render_rgb8_placed_signal_device(scene.handle, C.byref(p), frame_ptr, W * 3, flags_ptr, epoch[0], sptr))
+        # (the call publishes into d_flags[band_index]; with unequal spans band_index is a slot, not the rank)
+        rr.ffi.check(lib.rr_render_rgb8_placed_signal_device(scene.handle, C.byref(shard[0]), frame_ptr, W * 3,
+                                                             C.c_void_p(flags_ptr.value + 4 * (rank - shard[0].band_index)), epoch[0], sptr))
         if rank == 0:
             rr.ffi.check(lib.rr_fence_wait_device(local_rank, flags_ptr, world, epoch[0], 5000, status_ptr, sptr))
             return 2
         return 1
 
     def step_allreduce_fence():
-        rr.ffi.check(lib.rr_render_rgb8_placed_device(scene.handle, C.byref(p), frame_ptr, W * 3, sptr))
+        rr.ffi.check(lib.rr_render_rgb8_placed_device(scene.handle, C.byref(p_eq), frame_ptr, W * 3, sptr))
         dist.all_reduce(tok)  # completion fence: rank 0's stream passes it only after every rank's kernel
         return 1
 
     def step_gather():
-        scene.render_rgb8_device(p, packed.data_ptr(), stream=stream.cuda_stream)
+        scene.render_rgb8_device(p_eq, packed.data_ptr(), stream=stream.cuda_stream)
         glist = list(gathered.chunk(world)) if rank == 0 else None
-        dist.gather(packed, glist, dst=0)
+        dist.gather(packed[:shard_bytes], glist, dst=0)
         if rank == 0:
-            rr.ffi.check(lib.rr_bands_unpack_device(C.byref(p), C.c_void_p(gathered.data_ptr()), shard_bytes,
+            rr.ffi.check(lib.rr_bands_unpack_device(C.byref(p_eq), C.c_void_p(gathered.data_ptr()), shard_bytes,
                                                     C.c_void_p(gframe.data_ptr()), sptr))
             return 2
         return 1
+
+    shard = [p]
+    shares = None
+    single = None
+    same_1gpu_ms = None
+    if sharded:
+        # the SAME frame on one GPU in the same run (honest scaling base; also what the share chooser needs)
+        single = torch.empty(frame_bytes, dtype=torch.uint8, device=dev) if rank == 0 else None
+        if rank == 0:
+            sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(max(5, min(steps, 20)))]
+            for _ in range(3):
+                scene.render_rgb8_device(whole, single.data_ptr(), stream=stream.cuda_stream)
+            for a, b in sev:
+                c.flush.fill_(2)
+                a.record(stream)
+                scene.render_rgb8_device(whole, single.data_ptr(), stream=stream.cuda_stream)
+                b.record(stream)
+            torch.cuda.synchronize(dev)
+            same_1gpu_ms = sum(a.elapsed_time(b) for a, b in sev) / len(sev)
+        barrier(c)
+
+    def copy_rate(params):
+        """Raw NVLink ingress of rank 0: every other rank copies as many bytes as its shard holds from local memory into
+        rank 0's frame at the same time (plain cudaMemcpyAsync on peer memory), behind the same device-side barrier,
+        timed like the step (events, max over ranks). Returns (ms, bytes into rank 0)."""
+        n_bytes = rr.frame_rows(params) * W * 3
+        off = (rank * (frame_bytes // world)) // 256 * 256  # anywhere inside the frame (the bytes are overwritten by the next render)
+        off = min(off, frame_bytes - n_bytes)
+
+        def step_copy():
+            if rank != 0:  # rank 0 only receives
+                rr.ffi.check(lib.rr_device_copy(local_rank, C.c_void_p(frame_ptr.value + off), C.c_void_p(packed.data_ptr()), n_bytes, sptr))
+            return 0
+
+        cms, _, _, _ = timed(c, step_copy, 10, 3, False, device_barrier)
+        tot = torch.tensor([n_bytes if rank != 0 else 0], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot)
+        return cms, int(tot.item())
+
+    if sharded and not march and not c.args.equal_shares:
+        # Unequal shares. Every row rendered elsewhere enters rank 0 through ITS NVLink ports, rows it renders itself do
+        # not; when that ingress, not the kernels, bounds the step (8 GPUs, sub-millisecond frames), rank 0 should own more
+        # band slots than the others (rr_frame_params.band_span). Chosen here from two numbers measured in this run: the
+        # 1-GPU time of the frame and the raw ingress rate with equal shards.
+        cms, inbound = copy_rate(p_eq)
+        pick = [1, 1, None]
+        if rank == 0:
+            rate = inbound / cms  # bytes per ms
+            best = None
+            for b in (1, 2, 3, 4):
+                for a in range(b, 3 * b + 1):
+                    period = a + (world - 1) * b
+                    t0 = same_1gpu_ms * a / period + 0.022        # rank 0's kernel (+ the launch-size independent part)
+                    tr = same_1gpu_ms * b / period + 0.022
+                    tx = frame_bytes * (period - a) / period / rate + 0.012  # what has to cross into rank 0
+                    est = max(t0, tr, tx)
+                    if best is None or est < best[0] - 1e-4:
+                        best = (est, a, b)
+            pick = [best[1], best[2], best[0]]
+            if c.args.shares:
+                pick = [int(c.args.shares.split(",")[0]), int(c.args.shares.split(",")[1]), None]
+        dist.broadcast_object_list(pick, src=0)
+        if pick[0] != pick[1]:
+            spans, period = c.bands.weighted_spans(world, pick[0], pick[1])
+            shard[0] = ren.frame_params(band_rows, spans[rank][0], period, spans[rank][1])
+        shares = {"rank0_slots": pick[0], "other_slots": pick[1], "period_slots": pick[0] + (world - 1) * pick[1],
+                  "rank0_share": pick[0] / (pick[0] + (world - 1) * pick[1]), "predicted_step_ms": pick[2],
+                  "inputs": {"same_workload_1gpu_ms": same_1gpu_ms, "raw_ingress_ms_equal_shards": cms},
+                  "note": "rr_frame_params.band_span: rank 0 (the frame's owner) renders more band slots per period than the other ranks"}
+    p = shard[0]
+    my_rows = rr.frame_rows(p)
 
     ms_per_step, launches, clocks, wall_s = timed(c, step_main, steps, warmup, primary, device_barrier)
     value = rays / (ms_per_step * 1e-3) / 1e6
@@ -411,23 +485,9 @@ def measure(c, name, steps, warmup, primary):
     kernel_ms = float(kt.item())
 
     # ---- N>1: the SAME frame on one GPU in the same run (honest scaling base), alternatives, frame check ----
-    same_1gpu_ms = None
     alt = None
     frame_check = None
     if sharded:
-        single = torch.empty(frame_bytes, dtype=torch.uint8, device=dev) if rank == 0 else None
-        if rank == 0:
-            sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(max(5, min(steps, 20)))]
-            for _ in range(3):
-                scene.render_rgb8_device(whole, single.data_ptr(), stream=stream.cuda_stream)
-            for a, b in sev:
-                c.flush.fill_(2)
-                a.record(stream)
-                scene.render_rgb8_device(whole, single.data_ptr(), stream=stream.cuda_stream)
-                b.record(stream)
-            torch.cuda.synchronize(dev)
-            same_1gpu_ms = sum(a.elapsed_time(b) for a, b in sev) / len(sev)
-        barrier(c)
         if primary:
             gms, _, _, _ = timed(c, step_gather, max(5, steps // 2), warmup, False, device_barrier)
             ams, _, _, _ = timed(c, step_allreduce_fence, max(5, steps // 2), warmup, False, device_barrier)
@@ -462,20 +522,11 @@ def measure(c, name, steps, warmup, primary):
     # device-side barrier, timed like the step (events, max over ranks).
     nvlink = None
     if sharded and primary:
-        my_bytes = my_rows * W * 3
-        off = sum(rr.frame_rows(ren.frame_params(band_rows, r, world)) for r in range(rank)) * W * 3
-
-        def step_copy():
-            if rank != 0:  # rank 0 only receives
-                rr.ffi.check(lib.rr_device_copy(local_rank, C.c_void_p(frame_ptr.value + off), C.c_void_p(packed.data_ptr()), my_bytes, sptr))
-            return 0
-
-        cms, _, _, _ = timed(c, step_copy, 10, 3, False, device_barrier)
-        inbound = frame_bytes - rr.frame_rows(ren.frame_params(band_rows, 0, world)) * W * 3
+        cms, inbound = copy_rate(p)
         nvlink = {"bound": f"nvlink ingress of rank 0 ({world - 1} peers writing their shards at once, cudaMemcpyAsync)",
                   "bytes_into_rank0": inbound, "raw_copy_ms": cms, "raw_gbs": inbound / cms / 1e6,
                   "achieved_gbs": inbound / ms_per_step / 1e6, "frac": cms / ms_per_step,
-                  "note": "the step cannot be shorter than max(raw_copy_ms, ideal_kernel_ms): the kernel's own stores ARE the transfer"}
+                  "note": "the step cannot be shorter than max(raw_copy_ms, this frame's 1-GPU time x the largest share): the kernel's own stores ARE the transfer"}
         barrier(c)
 
     # ---- e2e: the reference-facing call, frame delivered to page-locked HOST memory ------------
@@ -499,7 +550,7 @@ def measure(c, name, steps, warmup, primary):
         rr.ffi.check(lib.rr_host_register(host, frame_bytes))
 
         def e2e_step():
-            rr.ffi.check(lib.rr_render_rgb8_placed(scene.handle, C.byref(p), host, 0))
+            rr.ffi.check(lib.rr_render_rgb8_placed(scene.handle, C.byref(p_eq), host, 0))
             dist.barrier()
 
     for _ in range(3):
@@ -515,7 +566,7 @@ def measure(c, name, steps, warmup, primary):
     e2e_value = rays / (e2e_ms * 1e-3) / 1e6
     # what bounds e2e: the frame has to cross PCIe once. Raw pinned D2H copy of the same bytes on the same box, measured
     # here: one GPU alone at N=1; at N>1 all ranks copy their share at the same time (aggregate rate of the box).
-    copy_bytes = frame_bytes if not sharded else my_rows * W * 3
+    copy_bytes = frame_bytes if not sharded else eq_rows * W * 3
     pin = torch.empty(max(1, copy_bytes), dtype=torch.uint8).pin_memory()
     src = torch.empty(max(1, copy_bytes), dtype=torch.uint8, device=dev)
     for _ in range(3):
@@ -631,7 +682,7 @@ def measure(c, name, steps, warmup, primary):
         "steps": steps, "ms_per_step": ms_per_step, "value": value, "unit": "Mrays/s", "kernel_ms": kernel_ms,
         "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_frame": e2e_ms, "h2d_bytes_per_step": C.sizeof(rr.ffi.rr_frame_params),
-                "d2h_bytes_per_step": my_rows * W * 3,
+                "d2h_bytes_per_step": (eq_rows if sharded else my_rows) * W * 3,
                 "api": ("rr_render_rgb8_placed (C ABI): each rank's bands -> one shared page-locked host frame, + barrier"
                         if sharded else "rr_render_rgb8 (C ABI) -> pinned host RGB8 frame"),
                 "check": e2e_check, "roofline": pcie},
@@ -646,9 +697,11 @@ def measure(c, name, steps, warmup, primary):
         res["per_rank_kernel_ms"] = kall
         res["ideal_kernel_ms"] = same_1gpu_ms / world
         res["frame_check"] = frame_check
+        if shares:
+            res["band_shares"] = shares
         if nvlink:
             res["nvlink_roofline"] = nvlink
-            res["step_lower_bound_ms"] = max(nvlink["raw_copy_ms"], same_1gpu_ms / world)
+            res["step_lower_bound_ms"] = max(nvlink["raw_copy_ms"], same_1gpu_ms * (shares["rank0_share"] if shares else 1.0 / world))
             res["efficiency_vs_bound"] = res["step_lower_bound_ms"] / ms_per_step
         if alt:
             res["alt"] = alt
@@ -752,6 +805,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="only the headline workload (no other BASELINE configs, no host-path timings)")
     ap.add_argument("--band-rows", type=int, default=None, help="rows per interleaved band of the multi-GPU shard (default 16)")
+    ap.add_argument("--equal-shares", action="store_true", help="N>1: every rank owns one band slot per period (no unequal band spans)")
+    ap.add_argument("--shares", default=None, help="N>1: force 'A,B' band slots per period for rank 0 / every other rank (default: chosen from measurements)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps or 10
@@ -800,7 +855,7 @@ def main():
             "wall_s_timed_region": r["_wall_s"],
         }
         for k in ("e2e_pageable", "same_workload_1gpu_ms", "efficiency_same_workload", "per_rank_kernel_ms", "ideal_kernel_ms", "frame_check",
-                  "nvlink_roofline", "step_lower_bound_ms", "efficiency_vs_bound", "alt"):
+                  "band_shares", "nvlink_roofline", "step_lower_bound_ms", "efficiency_vs_bound", "alt"):
             if k in r:
                 line[k] = r[k]
         if configs:

@@ -53,7 +53,7 @@ int main(int argc, char **argv) {
     p.cam_rotation[0] = -0.5f; p.cam_rotation[1] = -0.5f; p.cam_rotation[2] = -0.5f; p.cam_rotation[3] = 0.5f;
     const float l[3] = {50.0f, 60.0f, -50.0f}, ln = sqrtf(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
     for (int k = 0; k < 3; ++k) p.light[k] = l[k] / ln;
-    p.max_reflections = 3; p.max_refractions = 10; p.bg_kind = RR_BG_BGCOLOR; p.band_count = 1; p.band_rows = 1;
+    p.max_reflections = 3; p.max_refractions = 10; p.bg_kind = RR_BG_BGCOLOR; p.band_count = 1; p.band_rows = 1; p.band_span = 1;
 
     rr_scene *scene = NULL;
     void *frame = NULL;

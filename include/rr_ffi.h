@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define RR_ABI_VERSION 1
+#define RR_ABI_VERSION 2
 
 /* ------------------------------------------------------------------------------------------ */
 /* status codes                                                                                */
@@ -119,12 +119,16 @@ typedef struct rr_frame_params {
     int32_t max_reflections;    /* honoured by raytrace only (render.rs:1195 vs :1368) */
     int32_t max_refractions;
     int32_t bg_kind;            /* rr_bg_kind */
-    /* Row-band sharding (multi-GPU). Rows are grouped in bands of `band_rows`; band b belongs to
-     * shard (b % band_count); this call renders only the bands of shard `band_index`, packed
-     * contiguously in band order. band_count<=1 renders the whole frame. */
+    /* Row-band sharding (multi-GPU). Rows are grouped in bands of `band_rows`; band b sits in slot
+     * (b % band_count) of its period; this call renders only the bands whose slot is in
+     * [band_index, band_index + band_span), packed contiguously in band order. band_count<=1 renders
+     * the whole frame; band_span <= 1 is one slot per shard (equal shares). Unequal spans give a rank a
+     * larger share of the rows: the owner of a multi-GPU frame receives every other rank's rows over
+     * its NVLink ports, and rows it renders itself do not cross them. */
     int32_t band_rows;
     int32_t band_index;
     int32_t band_count;
+    int32_t band_span;
 } rr_frame_params;
 
 /* per-class ray counters written by rr_render_count (definition of "ray": SURVEY.md 8d) */
@@ -229,7 +233,8 @@ int rr_render_rgb8_placed_device(rr_scene *scene, const rr_frame_params *params,
 int rr_render_rgb8_placed(rr_scene *scene, const rr_frame_params *params, uint8_t *host_frame,
                           size_t row_stride);
 /* Fused completion for the device frame: no collective after the kernel. The render kernel itself publishes
- * `epoch` into d_flags[params->band_index] (a uint32 array of band_count words in the FRAME OWNER's memory,
+ * `epoch` into d_flags[params->band_index] (a uint32 array of band_count words in the FRAME OWNER's memory; with
+ * unequal band spans pass d_flags - band_index + <this shard's word>,
  * allocated with rr_device_alloc + rr_device_memset(0) and mapped by the other ranks like the frame) once all of
  * this shard's rows are in the frame: system-scope fence per block, last block does the release store
  * (both modes; an empty shard queues a one-thread publisher instead). The owner calls rr_fence_wait_device to make

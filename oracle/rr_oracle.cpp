@@ -690,7 +690,8 @@ std::vector<int32_t> shard_rows(const rr_frame_params *p) {
     const int32_t cnt = p->band_count <= 1 ? 1 : p->band_count;
     const int32_t br = p->band_rows <= 0 ? 1 : p->band_rows;
     for (int32_t iy = 0; iy < p->yres; ++iy) {
-        if (cnt == 1 || (iy / br) % cnt == p->band_index) rows.push_back(iy);
+        const int32_t slot = (iy / br) % cnt, span = p->band_span <= 1 ? 1 : p->band_span;
+        if (cnt == 1 || (slot >= p->band_index && slot < p->band_index + span)) rows.push_back(iy);
     }
     return rows;
 }

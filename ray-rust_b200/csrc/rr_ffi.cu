@@ -115,11 +115,13 @@ int32_t rows_of(const rr_frame_params *p) {
     const int br = p->band_rows <= 0 ? 1 : p->band_rows;
     // bands b = band_index, band_index+cnt, ...; each has br rows except a clipped last one
     int64_t rows = 0;
-    for (int64_t b = p->band_index; b * br < p->yres; b += cnt) {
-        int64_t lo = b * br, hi = lo + br;
-        if (hi > p->yres) hi = p->yres;
-        rows += hi - lo;
-    }
+    const int span = p->band_span <= 1 ? 1 : p->band_span;
+    for (int64_t b0 = p->band_index; b0 * br < p->yres; b0 += cnt)
+        for (int64_t b = b0; b < b0 + span && b * br < p->yres; ++b) {
+            int64_t lo = b * br, hi = lo + br;
+            if (hi > p->yres) hi = p->yres;
+            rows += hi - lo;
+        }
     return (int32_t)rows;
 }
 
@@ -127,7 +129,8 @@ int check_params(const rr_frame_params *p) {
     if (!p) return fail(RR_ERR_BAD_ARG, "params is null");
     if (p->xres < 0 || p->yres < 0) return fail(RR_ERR_BAD_ARG, "negative resolution");
     if ((int64_t)p->xres * (int64_t)p->yres > (int64_t)1 << 31) return fail(RR_ERR_BAD_ARG, "frame larger than 2^31 pixels");
-    if (p->band_count > 1 && (p->band_index < 0 || p->band_index >= p->band_count || p->band_rows <= 0))
+    if (p->band_count > 1 && (p->band_index < 0 || p->band_index >= p->band_count || p->band_rows <= 0 ||
+                              (p->band_span > 1 && p->band_index + p->band_span > p->band_count)))
         return fail(RR_ERR_BAD_ARG, "bad row-band parameters");
     if (p->bg_kind != RR_BG_BGCOLOR && p->bg_kind != RR_BG_BLACK) return fail(RR_ERR_BAD_ARG, "unknown bg_kind");
     if (p->max_refractions > rr::RR_MAX_STACK_HOST)
@@ -146,6 +149,7 @@ rr::FrameParams to_dev(const rr_frame_params *p, const rr_scene *s) {
     d.band_count = p->band_count <= 1 ? 1 : p->band_count;
     d.band_rows = p->band_rows <= 0 ? 1 : p->band_rows;
     d.band_index = d.band_count == 1 ? 0 : p->band_index;
+    d.band_span = d.band_count == 1 || p->band_span <= 1 ? 1 : p->band_span;
     d.local_rows = rows_of(p);
     d.row0 = 0;
     if (s) rr::finish_frame_params(d, s->H);
@@ -715,6 +719,7 @@ int rr_bands_unpack_device(const rr_frame_params *params, const void *d_packed, 
     int rc = check_params(params);
     if (rc) return rc;
     rr::FrameParams P = to_dev(params, nullptr);
+    if (P.band_span > 1) return fail(RR_ERR_UNSUPPORTED, "rr_bands_unpack_device: equal band spans only");
     cudaError_t e = rr::launch_bands_unpack(P, d_packed, shard_stride_bytes, d_frame, reinterpret_cast<cudaStream_t>(cuda_stream));
     if (e != cudaSuccess) return fail_cuda(e, "bands_unpack");
     if (!cuda_stream) CU(cudaStreamSynchronize(nullptr));
@@ -793,6 +798,7 @@ int rr_render_rgb8_placed(rr_scene *s, const rr_frame_params *params, uint8_t *h
     if (rc) return rc;
     CU(cudaSetDevice(s->device));
     rr::FrameParams P = to_dev(params, s);
+    if (P.band_span > 1) return fail(RR_ERR_UNSUPPORTED, "rr_render_rgb8_placed: unequal band spans are a device-frame feature");
     const size_t packed = (size_t)P.xres * 3;
     if (row_stride == 0) row_stride = packed;
     if (row_stride < packed) return fail(RR_ERR_BAD_ARG, "row_stride smaller than a row");

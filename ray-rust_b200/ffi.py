@@ -85,6 +85,7 @@ class rr_frame_params(C.Structure):
         ("band_rows", C.c_int32),
         ("band_index", C.c_int32),
         ("band_count", C.c_int32),
+        ("band_span", C.c_int32),
     ]
 
 

@@ -98,7 +98,7 @@ rr_frame_params RenderEnv::frame_params() const {
     p.glow_effect = glow_some_ ? glow_value_ : 0.0f;
     p.max_reflections = max_reflections; p.max_refractions = max_refractions;
     p.bg_kind = bgproc == BgProc::BgColor ? RR_BG_BGCOLOR : RR_BG_BLACK;
-    p.band_rows = 0; p.band_index = 0; p.band_count = 1;
+    p.band_rows = 0; p.band_index = 0; p.band_count = 1; p.band_span = 1;
     return p;
 }
 

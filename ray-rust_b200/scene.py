@@ -407,7 +407,7 @@ class RenderEnv:  # render.rs:646-799
         desc = ffi.rr_scene_desc(len(self._objects), co, len(mats), cm, len(textures), ct)
         return FlatScene(desc, [cm, co, ct, keep])
 
-    def frame_params(self, band_rows=0, band_index=0, band_count=1):
+    def frame_params(self, band_rows=0, band_index=0, band_count=1, band_span=1):
         p = ffi.rr_frame_params()
         p.xres, p.yres, p.xfov, p.yfov = self.xres, self.yres, float(self.xfov), float(self.yfov)
         p.cam_position[:] = [float(x) for x in self.camera.position]
@@ -418,7 +418,7 @@ class RenderEnv:  # render.rs:646-799
         p.glow_effect = 0.0 if self._glow_effect is None else float(self._glow_effect)
         p.max_reflections, p.max_refractions = self.max_reflections, self.max_refractions
         p.bg_kind = ffi.RR_BG_BGCOLOR if self.bgproc == "bgcolor" else ffi.RR_BG_BLACK
-        p.band_rows, p.band_index, p.band_count = band_rows, band_index, band_count
+        p.band_rows, p.band_index, p.band_count, p.band_span = band_rows, band_index, band_count, band_span
         return p
 
 
@@ -434,7 +434,8 @@ def frame_rows(params):
     if cnt == 1:
         return params.yres
     br = max(1, params.band_rows)
-    return sum(1 for iy in range(params.yres) if (iy // br) % cnt == params.band_index)
+    span = max(1, params.band_span)
+    return sum(1 for iy in range(params.yres) if params.band_index <= (iy // br) % cnt < params.band_index + span)
 
 
 class DeviceScene:

@@ -98,7 +98,7 @@ FrameParams to_dev(const rr_frame_params *p, const SceneHead &H) {
     for (int k = 0; k < 4; ++k) d.cam_rot[k] = p->cam_rotation[k];
     d.use_raymarching = p->use_raymarching; d.glow_enabled = p->glow_enabled; d.glow_effect = p->glow_effect;
     d.max_reflections = p->max_reflections; d.max_refractions = p->max_refractions; d.bg_kind = p->bg_kind;
-    d.band_count = 1; d.band_rows = 1; d.band_index = 0; d.local_rows = p->yres; d.row0 = 0; d.placed = 0;
+    d.band_count = 1; d.band_rows = 1; d.band_index = 0; d.band_span = 1; d.local_rows = p->yres; d.row0 = 0; d.placed = 0;
     finish_frame_params(d, H);
     g_ptab.clear();
     for (int ix = 0; ix < d.xres; ++ix) g_ptab.push_back(prim_col_entry(d, ix));

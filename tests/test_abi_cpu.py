@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(rr):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in rr_ffi.h but not exported"
     assert sorted(rr.ffi.PROTOTYPES) == syms
-    assert lib.rr_abi_version() == 1
+    assert lib.rr_abi_version() == 2
 
 
 def test_integration_sys_block_lists_every_symbol():
@@ -185,3 +185,13 @@ def test_frame_rows(rr):
         assert n.value == rr.frame_rows(p)
         tot += n.value
     assert tot == 70
+    tot = 0
+    for idx, span in ((0, 3), (3, 2), (5, 2)):  # unequal spans of a 7-slot period
+        p = ren.frame_params(band_rows=4, band_index=idx, band_count=7, band_span=span)
+        n = C.c_int32()
+        assert rr.ffi.load().rr_frame_rows(C.byref(p), C.byref(n)) == 0
+        assert n.value == rr.frame_rows(p)
+        tot += n.value
+    assert tot == 70
+    bad = ren.frame_params(band_rows=4, band_index=5, band_count=7, band_span=3)  # span runs past the period
+    assert rr.ffi.load().rr_frame_rows(C.byref(bad), C.byref(n)) == rr.ffi.RR_ERR_BAD_ARG

@@ -167,3 +167,16 @@ def test_band_sharding_oracle(oracle, rr):
         ys = [y for y in range(70) if (y // 8) % 3 == k]
         out[ys] = rows[k]
     assert np.array_equal(out, full)
+    # unequal shares (band_span): rank 0 owns 2 of every 4 band slots, ranks 1 and 2 one each
+    from ray_rust_b200 import bands
+    spans, period = bands.weighted_spans(3, 2, 1)
+    assert spans == [(0, 2), (2, 1), (3, 1)] and period == 4
+    out2, tot = np.zeros_like(full), 0
+    for idx, span in spans:
+        p = ren.frame_params(band_rows=8, band_index=idx, band_count=period, band_span=span)
+        got = oracle.render(ren, params=p)["u8"]
+        ys = bands.span_rows(70, 8, idx, span, period)
+        assert got.shape[0] == len(ys) == rr.frame_rows(p)
+        out2[ys] = got
+        tot += len(ys)
+    assert tot == 70 and np.array_equal(out2, full)

@@ -104,6 +104,39 @@ def test_placed_signal_and_fence_wait(rr, n, w, h, march):
     scene.close()
 
 
+@pytest.mark.parametrize("w,h,march,synth", [(640, 360, False, False), (256, 150, True, False), (256, 144, False, True)])
+def test_placed_unequal_band_spans(rr, w, h, march, synth):
+    """rr_frame_params.band_span: the frame's owner renders a larger share (3 of every 8 band slots, five other shards one
+    each). Placed, signalled launches of all shards must assemble the 1-GPU frame; packed launches must hold exactly the
+    shard's rows; the host-frame and un-interleave paths refuse unequal spans."""
+    import torch
+    from ray_rust_b200 import bands
+
+    ren = rr.synthetic_scene(w, h, n_spheres=64) if synth else rr.default_scene(w, h, use_raymarching=march, glow_effect=1.0 if march else None)
+    scene = rr.DeviceScene(ren, 0)
+    lib = scene.lib
+    full = scene.render_rgb8(ren.frame_params())
+    spans, period = bands.weighted_spans(6, 3, 1)
+    frame = torch.zeros(h * w * 3, dtype=torch.uint8, device="cuda:0")
+    flags = torch.zeros(8, dtype=torch.int32, device="cuda:0")
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for r, (idx, span) in enumerate(spans):
+        p = ren.frame_params(4, idx, period, span)
+        word = C.c_void_p(flags.data_ptr() + 4 * (r - idx))   # rr_ffi.h: d_flags[band_index] is written
+        rr.ffi.check(lib.rr_render_rgb8_placed_signal_device(scene.handle, C.byref(p), C.c_void_p(frame.data_ptr()), 0, word, 7, C.c_void_p(st.cuda_stream)))
+        packed = scene.render_rgb8(p)
+        assert np.array_equal(packed, full[bands.span_rows(h, 4, idx, span, period)])
+    torch.cuda.synchronize()
+    assert flags.cpu().tolist() == [7] * 6 + [0, 0]
+    assert np.array_equal(frame.cpu().numpy().reshape(h, w, 3), full)
+    p = ren.frame_params(4, 0, period, 3)
+    host = np.zeros((h, w, 3), dtype=np.uint8)
+    assert lib.rr_render_rgb8_placed(scene.handle, C.byref(p), host.ctypes.data_as(C.c_void_p), 0) == rr.ffi.RR_ERR_UNSUPPORTED
+    assert lib.rr_bands_unpack_device(C.byref(p), C.c_void_p(frame.data_ptr()), 0, C.c_void_p(frame.data_ptr()), None) == rr.ffi.RR_ERR_UNSUPPORTED
+    scene.close()
+
+
 @pytest.mark.parametrize("kind", ["march", "synthetic"])
 def test_zero_copy_pinned_host_frame(rr, kind):
     """Long kernels store straight into a page-locked host frame (no device buffer, no DMA copy); the bytes must equal

@@ -441,9 +441,11 @@ def measure(c, name, steps, warmup, primary):
             for b in (1, 2, 3, 4):
                 for a in range(b, 3 * b + 1):
                     period = a + (world - 1) * b
-                    t0 = same_1gpu_ms * a / period + 0.022        # rank 0's kernel (+ the launch-size independent part)
-                    tr = same_1gpu_ms * b / period + 0.022
-                    tx = frame_bytes * (period - a) / period / rate + 0.012  # what has to cross into rank 0
+                    # (+ 0.030 ms: what a shard launch and the transfer path take beyond their proportional part, fitted to
+                    #  the 8-GPU records profiles/r2t_bench_n8*.json: equal shares 0.148 ms, 4/3 0.1425, 5/4 0.1418)
+                    t0 = same_1gpu_ms * a / period + 0.030        # rank 0's kernel
+                    tr = same_1gpu_ms * b / period + 0.030
+                    tx = frame_bytes * (period - a) / period / rate + 0.030  # what has to cross into rank 0
                     est = max(t0, tr, tx)
                     if best is None or est < best[0] - 1e-4:
                         best = (est, a, b)

@@ -59,6 +59,8 @@ def main():
         h = src[heads[k]]
         end = heads[k + 1] - 1 if k + 1 < len(heads) else len(src)
         ci, si = h.index("Instructions Executed"), h.index("Source")
+        ti = h.index("Predicated-On Thread Instructions Executed") if "Predicated-On Thread Instructions Executed" in h else None
+        tops = collections.Counter()
         for r in src[heads[k] + 1:end]:
             if len(r) <= ci:
                 continue
@@ -70,9 +72,14 @@ def main():
             m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[si])
             ops[m.group(2).split(".")[0] if m else "?"] += n
             total += n
+            if ti is not None and len(r) > ti and r[ti].isdigit():
+                tops[m.group(2).split(".")[0] if m else "?"] += int(r[ti])
     summary["sass_instructions"] = n_sass
     summary["warp_instructions_executed"] = total
     summary["opcode_mix_pct"] = {o: round(100.0 * n / total, 2) for o, n in ops.most_common(25)} if total else {}
+    if heads:
+        # thread-level (predicated-on) counts of the FP32 opcodes: ncu's op_ffma counter does not include the packed FFMA2
+        summary["thread_inst_fp32"] = {o: tops.get(o, 0) for o in ("FADD", "FMUL", "FFMA", "FFMA2", "FMNMX", "FMNMX3", "MUFU")}
     json.dump(summary, open(out + ".json", "w"), indent=1)
     with open(out + ".md", "w") as f:
         f.write(f"# ncu summary: {summary['kernel']}\n\nsource: `{rep}` (ncu --set full --clock-control none --import-source on)\n\n")

@@ -8,20 +8,23 @@ UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 out = {}
 for wl, nm in names.items():
     rel = f"profiles/{tag}_{nm}.json"
-    m = json.load(open(os.path.join(ROOT, rel)))["metrics"]
+    summ = json.load(open(os.path.join(ROOT, rel)))
+    m = summ["metrics"]
     val = lambda k: float(m[k]["value"])
     rd = val("dram__bytes_read.sum") * UNIT[m["dram__bytes_read.sum"]["unit"]]
     wr = val("dram__bytes_write.sum") * UNIT[m["dram__bytes_write.sum"]["unit"]]
     cyc = val("sm__cycles_elapsed.max")
     per = lambda op: val(f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed")
-    ex = (per("fadd") + per("fmul") + 2 * per("ffma")) * cyc
+    ffma2 = summ.get("thread_inst_fp32", {}).get("FFMA2", 0)  # not in ncu's op_ffma counter; two FP32 operations per thread
+    ex = (per("fadd") + per("fmul") + 2 * per("ffma")) * cyc + 2 * ffma2
     out[wl] = {
         "dram_bytes_per_launch": int(rd + wr),
         "note": f"ncu --set full ({rel[:-5]}.md): dram__bytes_read {rd/1e6:.2f} MB + dram__bytes_write {wr/1e6:.2f} MB per launch "
                 f"(kernel {m['gpu__time_duration.sum']['value']} {m['gpu__time_duration.sum']['unit']} under ncu); the RGB8 frame is stored once and is "
                 "still (partly) resident in the 126 MB L2 when the kernel ends",
         "executed_flops_per_launch": int(ex),
-        "executed_note": f"ncu ({rel}): thread-level (FADD + FMUL + 2 x FFMA/FFMA2-slot) per elapsed cycle x sm__cycles_elapsed.max",
+        "executed_note": f"ncu ({rel}): thread-level (FADD + FMUL + 2 x FFMA) per elapsed cycle x sm__cycles_elapsed.max + 2 x thread-level FFMA2 of the SASS page "
+                         f"({ffma2} packed instructions: two FP32 operations each, not in ncu's op_ffma counter)",
     }
 json.dump(out, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))

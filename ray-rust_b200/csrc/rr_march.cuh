@@ -370,7 +370,7 @@ __device__ __forceinline__ V3 march_pixel(const DevScene &G, const SceneHead &H,
             lev += 1;  // render.rs:1317
             ro = pos; rd = eye; rig = ig;
         } else {
-            ro = pt + (light * F32_EPSILON);  // render.rs:1034
+            ro = pt + mk(P.light_eps[0], P.light_eps[1], P.light_eps[2]);  // pt + light * EPSILON, render.rs:1034 (frame constant)
             rd = light; rig = hidx;
         }
         const MarchResult r = raymarch_single<GLOW, MBVH>(H, S, K, ro, rd, rig, !shadow_phase, shadow_phase ? RR_INF : mmd);

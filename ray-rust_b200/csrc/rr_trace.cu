@@ -123,7 +123,8 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
     // Tried and dropped in round 2 (profiles/r2i_shard_time.txt, r2h_bench_n8_tail*.json): a smaller static share for small
     // launches and handing the last macro tiles out as their four 32x1 sub-tiles. Neither changes the time of a 1/8-frame
     // launch (0.105 ms against 0.082 ideal at 8K: that gap is not the tile schedule), and the 96-byte stores of the sub-tiles
-    // cost the 8-GPU step 5 % of its NVLink store rate.
+    // cost the 8-GPU step 5 % of its NVLink store rate. Issuing the queue grab for the NEXT tile before the current one is rendered
+    // (to hide the atomic's round trip: 1.2 % of warp time in ncu) is slower, 0.168 -> 0.177 ms at 4K (profiles/r2w_ab_trace.txt).
     constexpr int STATIC_16THS = BVH ? 6 : 8;
     const int n_static = sig.work ? (int)(((long long)ntiles * STATIC_16THS) >> 4) : ntiles;
     int nt = gw;

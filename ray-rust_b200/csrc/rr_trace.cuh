@@ -110,6 +110,9 @@ __device__ __forceinline__ void sphere_test(const float4 &c4, OiFn get_oi, const
 #ifndef RR_GROUP_FINISH
 #define RR_GROUP_FINISH 1
 #endif
+#ifndef RR_INIT_SHADING_STATE
+#define RR_INIT_SHADING_STATE 0  // 1: A/B build with start values for the shading state carried across the shadow ray
+#endif
 struct PairDQ { F2 D, q; };
 __device__ __forceinline__ F2 dot2(const PackK &K, const F2 &ax, const F2 &ay, const F2 &az, const F2 &bx, const F2 &by, const F2 &bz) {
     return add2(K, add2(K, mul2(K, ax, bx), mul2(K, ay, by)), mul2(K, az, bz));  // (x*x' + y*y') + z*z'
@@ -525,10 +528,18 @@ __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneHead &H,
     TraceFrame stack[RR_MAX_STACK];
     int ray_class = 0;  // 0 primary, 1 refract child's first ray, 2 reflect continuation
     // shading() state carried across the shadow ray
+    // (hidx, pt, n and the two intensities are written by the first half of shading() before its second half reads them;
+    // giving them start values would cost a register move each per pixel at the loop entry)
     bool shadow_phase = false;  // which kind of ray produced `h`
+#if RR_INIT_SHADING_STATE
     int hidx = 0;
     V3 pt = vi, n = vi;
     float diffuse_intensity = 0.0f, reflection_intensity = 0.0f;
+#else
+    int hidx;
+    V3 pt, n;
+    float diffuse_intensity, reflection_intensity;
+#endif
     if (COUNT) {
         cnt.pixels++;
         cnt.primary++;
@@ -677,7 +688,7 @@ __device__ __forceinline__ V3 trace_pixel(const DevScene &G, const SceneHead &H,
                 else cnt.reflect++;
             }
         } else {
-            ro = pt + (light * F32_EPSILON);  // render.rs:1034
+            ro = pt + mk(P.light_eps[0], P.light_eps[1], P.light_eps[2]);  // pt + light * EPSILON, render.rs:1034 (the product is a frame constant)
             rd = light; rig = hidx; rfl = 0u;
             if (COUNT) {
                 cnt.shadow++;

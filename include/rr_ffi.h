@@ -276,6 +276,11 @@ int rr_last_kernel_ms(rr_scene *scene, float *ms);
  * FFMA chain on every SM and reports achieved TFLOP/s. */
 int rr_fp32_peak_tflops(int device, float *unfused_tflops, float *ffma_tflops);
 
+/* Device self-test of Vec3::normalized (vec3.rs:36-39) as the kernels compute it: the three IEEE divisions share one
+ * refined reciprocal of the length (csrc/rr_device.cuh). Runs `n` hashed vectors (special values included) through that
+ * path and through three plain divisions and reports the number that differ in any bit; 0 is the only passing value. */
+int rr_selftest_normalize(int device, uint64_t n, uint64_t seed, uint64_t *mismatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -943,4 +943,13 @@ int rr_fp32_peak_tflops(int device, float *unfused_tflops, float *ffma_tflops) {
     return RR_OK;
 }
 
+int rr_selftest_normalize(int device, uint64_t n, uint64_t seed, uint64_t *mismatches) {
+    if (!mismatches) return fail(RR_ERR_BAD_ARG, "null output");
+    unsigned long long bad = 0;
+    cudaError_t e = rr::normalize_selftest(device, (unsigned long long)n, (unsigned long long)seed, &bad);
+    if (e != cudaSuccess) return fail_cuda(e, "normalize_selftest");
+    *mismatches = (uint64_t)bad;
+    return RR_OK;
+}
+
 }  // extern "C"

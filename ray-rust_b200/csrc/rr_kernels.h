@@ -35,6 +35,9 @@ cudaError_t launch_signal(const Signal &sig, cudaStream_t stream);
 cudaError_t preload_signal_kernels();
 cudaError_t launch_fence_wait(const unsigned *d_flags, int count, unsigned epoch, unsigned timeout_ms, unsigned *d_status,
                               cudaStream_t stream);
+// normalized() self-test: number of vectors (of n hashed ones) on which the shared-reciprocal path and three plain IEEE
+// divisions differ in any bit.
+cudaError_t normalize_selftest(int device, unsigned long long n, unsigned long long seed, unsigned long long *mismatches);
 // FP32 pipe calibration (roofline denominator): achieved TFLOP/s of unfused FMUL+FADD and of FFMA.
 cudaError_t fp32_peak(int device, float *unfused_tflops, float *ffma_tflops);
 

@@ -4,6 +4,10 @@
 // rays run the 10 001-iteration cap and hold 74 % of all iterations, concentrated in the horizon
 // rows), so tiles are handed out dynamically: each warp of a persistent grid pulls the next 8x4
 // pixel tile from a global atomic counter when it finishes one.
+// The ray-march kernel keeps plain IEEE divisions (SharedRcp, rr_device.cuh): its frame time is bound by the longest
+// dependent march chains, not by instruction issue, and the shared-reciprocal build measured 1 % slower here
+// (6.21 -> 6.29 ms at 4K, profiles/r2y_ab.txt) where the trace kernels gain 3-5 %.
+#define RR_SHARED_RCP 0
 #include "rr_kernels.h"
 #include "rr_march.cuh"
 

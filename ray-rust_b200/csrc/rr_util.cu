@@ -102,6 +102,49 @@ cudaError_t preload_signal_kernels() {
     return cudaFuncGetAttributes(&a, fence_wait_kernel);
 }
 
+// ---- self-test of normalized() (rr_device.cuh): shared-reciprocal path against three plain IEEE divisions -----------
+// Operands: a counter-based hash gives three floats with independent signs, mantissas and exponents; every 8th vector gets
+// exponents from the whole f32 range (zero, subnormal, huge, infinite and NaN components included) so that the guard and the
+// plain-division branch are exercised too, the others stay within 2^-44 .. 2^44 around the guard's limits.
+__device__ __forceinline__ unsigned st_hash(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return (unsigned)x;
+}
+__global__ void normalize_selftest_kernel(unsigned long long n, unsigned long long seed, unsigned long long *mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        float c[3];
+        const bool wild = (i & 7ull) == 7ull;
+        for (int k = 0; k < 3; ++k) {
+            const unsigned h = st_hash(seed + 3ull * i + k), h2 = st_hash(~seed + 5ull * i + k);
+            const unsigned ex = wild ? (h2 % 256u) : (127u - 44u + h2 % 89u);
+            c[k] = __uint_as_float((h & 0x807fffffu) | (ex << 23));
+            if (!wild && (h2 >> 28) == 0u) c[k] = c[(k + 1) % 3] * 0.0f + c[k] * 1e-3f;  // some strongly unequal magnitudes
+        }
+        const V3 v = mk(c[0], c[1], c[2]);
+        const V3 a = normalized(v), b = normalized_plain(v);
+        if (__float_as_uint(a.x) != __float_as_uint(b.x) || __float_as_uint(a.y) != __float_as_uint(b.y) || __float_as_uint(a.z) != __float_as_uint(b.z)) ++bad;
+        // the same three numbers as (numerator, numerator, divisor) of div_pair(): quotients far from 1
+        float u, w;
+        div_pair(c[0], c[1], c[2], u, w);
+        if (__float_as_uint(u) != __float_as_uint(c[0] / c[2]) || __float_as_uint(w) != __float_as_uint(c[1] / c[2])) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+cudaError_t normalize_selftest(int device, unsigned long long n, unsigned long long seed, unsigned long long *mismatches) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return e;
+    unsigned long long *d = nullptr;
+    e = cudaMalloc(&d, sizeof *d);
+    if (e != cudaSuccess) return e;
+    cudaMemset(d, 0, sizeof *d);
+    normalize_selftest_kernel<<<1184, 256>>>(n, seed, d);
+    e = cudaMemcpy(mismatches, d, sizeof *d, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 // ---- FP32 pipe calibration -------------------------------------------------------------------
 // 8 independent dependency chains per thread so the 4-cycle FMA-pipe latency is covered at
 // 16 warps/SMSP. FUSED=false compiles (under -fmad=false) to FMUL+FADD pairs: the instruction mix

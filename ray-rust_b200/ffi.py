@@ -149,6 +149,7 @@ PROTOTYPES = {
     "rr_host_free": (C.c_int, [_P]),
     "rr_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "rr_fp32_peak_tflops": (C.c_int, [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "rr_selftest_normalize": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
 }
 
 _lib = None

@@ -127,3 +127,16 @@ def test_many_cameras_one_handle(rr, oracle):
             g2 = scene.render_rgb8(small.frame_params())
             assert np.abs(g2.astype(int) - oracle.render(small, threads=NCPU)["u8"].astype(int)).max() <= 1
     scene.close()
+
+
+def test_shared_reciprocal_divisions_equal_ieee_divisions(rr):
+    """normalized() and get_uv() share one refined reciprocal per divisor (csrc/rr_device.cuh SharedRcp); the device
+    self-test runs 2^26 hashed operand sets (zeros, subnormals, huge values, infinities and NaN included) through that
+    path and through plain `/` and counts the sets that differ in any bit."""
+    import ctypes as C
+
+    lib = rr.ffi.load()
+    for seed in (1, 20261018):
+        bad = C.c_uint64(1)
+        rr.ffi.check(lib.rr_selftest_normalize(0, 1 << 26, seed, C.byref(bad)))
+        assert bad.value == 0

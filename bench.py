@@ -246,7 +246,14 @@ def setup(args):
     c.dev = torch.device("cuda", c.local_rank)
     torch.cuda.set_device(c.dev)
     c.lib = rr.ffi.load()
-    c.stream = torch.cuda.current_stream(c.dev)
+    # Everything timed runs on ONE explicit, non-default CUDA stream: the L2 flush, the events and the render launches. (The
+    # default stream's handle is 0, which the C ABI reads as "no caller stream: use the handle's own stream and block" — the
+    # launch would then run beside the flush on another stream and the events would bracket a host-side wait. The records
+    # up to profiles/r2u_* were taken that way and read ~8 us too long per step; profiles/r2z_flush_gap.txt.)
+    c.stream = torch.cuda.Stream(device=c.dev)
+    torch.cuda.set_stream(c.stream)
+    if not c.stream.cuda_stream:
+        raise SystemExit("bench.py needs a non-default CUDA stream")
     c.sptr = C.c_void_p(c.stream.cuda_stream)
     c.flush = torch.empty(256 << 20, dtype=torch.uint8, device=c.dev)  # > 126 MB L2
     c.sharded = c.world > 1
@@ -844,6 +851,7 @@ def main():
             "config": {"workload": name, "width": W, "height": H, "mode": r["mode"],
                        "max_reflections": 3, "max_refractions": 10, "rays_per_frame": r["rays_per_frame"], "ray_classes": r["_counts"],
                        "l2": "flushed between timed steps (256 MiB write, untimed)",
+                       "stream": "one non-default CUDA stream carries the flush, the events and the render launches",
                        "parallelism": f"row-bands{c.world}x{c.band_rows}, kernel stores rows AND its completion word into rank 0's memory over NVLink (CUDA IPC), rank 0 waits on the words; no collective"
                        if c.sharded else "1gpu",
                        "scene_resident": True},

@@ -15,6 +15,9 @@ namespace rr {
 #define RR_TRACE_THREADS 256
 #endif
 constexpr int TRACE_THREADS = RR_TRACE_THREADS;
+#ifndef RR_BYTE_STAGE
+#define RR_BYTE_STAGE 1  // 0: A/B build that assembles the 24 words of a sub-run with shuffles (profiles/r3c_ab.txt: 0.163 -> 0.156 ms at 4K with 1)
+#endif
 #ifndef RR_TRACE_MIN_BLOCKS
 #define RR_TRACE_MIN_BLOCKS 4
 #endif
@@ -157,9 +160,19 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
                 const int orow = P.placed ? irow : ly;
                 const float4 prow = __ldg(&P.ptab[P.xres + irow]);  // one row: the same for the four sub-tiles
                 unsigned *wb = reinterpret_cast<unsigned *>(rr_wbuf[threadIdx.x >> 5]);
+#if RR_BYTE_STAGE
+                const unsigned wb_s = (unsigned)__cvta_generic_to_shared(wb);
+#endif
 #pragma unroll 1
                 for (int sub = 0; sub < SUB; ++sub) {
                     const V3 c = trace_pixel<COUNT, BVH, HEADONLY, BVH && STAGE && RR_BVH_ORDERED>(G, H, S, P, primary_dir_tab(P, __ldg(&P.ptab[x0 + sub * 32 + lane]), prow), cnt);
+#if RR_BYTE_STAGE
+                    // every lane puts its own three bytes into the warp's staging run (3 byte stores; the 4 lanes that share a
+                    // 32-bit word serialise, which costs less than assembling words with two shuffles and a 64-bit shift)
+                    const unsigned qr = quantize(c.x), qg = quantize(c.y), qb = quantize(c.z);
+                    const unsigned a = wb_s + (unsigned)(sub * 96 + 3 * lane);
+                    asm volatile("st.shared.u8 [%0], %1;\n\tst.shared.u8 [%0+1], %2;\n\tst.shared.u8 [%0+2], %3;" ::"r"(a), "r"(qr), "r"(qg), "r"(qb) : "memory");
+#else
                     const unsigned rgb = quantize(c.x) | (quantize(c.y) << 8) | (quantize(c.z) << 16);
                     // word w of the 96-byte sub-run holds bytes 4w..4w+3 = pixels pa (and pa+1); lanes 0..23 own one word
                     const int pa = (4 * lane) / 3;
@@ -167,6 +180,7 @@ trace_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
                     const unsigned vb = __shfl_sync(0xffffffffu, rgb, min(pa + 1, 31));
                     const unsigned long long both = (unsigned long long)va | ((unsigned long long)vb << 24);
                     if (lane < 24) wb[sub * 24 + lane] = (unsigned)(both >> (8 * ((4 * lane - 3 * pa) & 3)));
+#endif
                 }
                 __syncwarp();
                 if (lane < 24)

@@ -254,13 +254,15 @@ int pick_chunks(size_t bytes, const rr::FrameParams &P, const rr_scene *s) {
 }
 
 // Row counts of the chunks (whole 4-row tiles): a geometric plan. The first chunk is rows/d, so that the first copy starts
-// after ~1/48 of the kernel work, every next one g times larger, so that the copy engine sees ~9 copies instead of 16
-// (a ~1.5 us gap each) while kernel k+1 (g x the rows at ~100 GB/s-equivalent) still ends before copy k (56 GB/s) does.
+// after ~1/d of the kernel work, every next one g times larger, so that the copy engine sees ~9 copies instead of 16
+// (a ~1.5 us gap each) while kernel k+1 (g x the rows at ~150 GB/s-equivalent) still ends before copy k (56 GB/s) does.
 // Measured against the uniform 16 x 1.5 MB plan (tools/ab_e2e_geom.py): 4K 0.523-0.531 -> 0.496-0.498 ms, 8K 1.88-1.92 ->
-// 1.86 ms; g = 2 is slower (the kernel falls behind the copy). RR_E2E_GEOM="d,g" overrides, "0" selects the uniform plan.
+// 1.86 ms with d = 48, g = 1.5 (round 1, 0.22 ms kernel); with the 0.156 ms kernel of round 2 a smaller first chunk and a
+// steeper plan win: d = 96, g = 1.7 gives 0.492-0.495 ms / 1.81-1.82 ms (profiles/r3e_e2e_geom.txt; raw copy 0.441 / 1.765).
+// RR_E2E_GEOM="d,g" overrides, "0" selects the uniform plan.
 int plan_chunks(int rows, int nchunk, int *plan) {
-    static const double geom_d = [] { const char *e = getenv("RR_E2E_GEOM"); return e ? atof(e) : 48.0; }();
-    static const double geom_g = [] { const char *e = getenv("RR_E2E_GEOM"); const char *c = e ? strchr(e, ',') : nullptr; return c ? atof(c + 1) : 1.5; }();
+    static const double geom_d = [] { const char *e = getenv("RR_E2E_GEOM"); return e ? atof(e) : 96.0; }();
+    static const double geom_g = [] { const char *e = getenv("RR_E2E_GEOM"); const char *c = e ? strchr(e, ',') : nullptr; return c ? atof(c + 1) : 1.7; }();
     int n = 0, done = 0;
     if (geom_d >= 2.0 && nchunk > 1) {
         double want = rows / geom_d;

@@ -16,7 +16,7 @@ for (w,h) in ((3840,2160),(7680,4320)):
     ts.sort(); print("%%dx%%d median %%.3f ms min %%.3f ms" %% (w,h,ts[20]*1e3, ts[0]*1e3), end="; ")
 print()
 ''' % root
-plans = [None, "64,1.5", "48,1.5", "32,1.5", "64,1.3", "32,1.3", "64,2.0", "24,1.4", "96,1.4"]
+plans = [None, "48,1.5", "64,1.7", "96,1.7", "96,2.0", "128,1.8", "64,2.0", "192,2.0", "32,1.5"]
 for rep in range(2):
     for g in plans:
         env = dict(os.environ)

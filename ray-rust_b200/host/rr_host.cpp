@@ -55,13 +55,13 @@ RenderMaterial::RenderMaterial(std::string name, RenderColor diffuse, RenderColo
 
 RenderMaterial &RenderMaterial::texture(const std::string &file) {  // render.rs:165-174
     texture_name_ = file;
-    texture_ = load_png_rgb8(file);
+    texture_ = load_image_rgb8(file);
     if (!texture_) throw std::runtime_error("texture image file load failed");
     return *this;
 }
 RenderMaterial &RenderMaterial::texture_ok(const std::string &file) {  // render.rs:177-181
     texture_name_ = file;
-    texture_ = load_png_rgb8(file);
+    texture_ = load_image_rgb8(file);
     return *this;
 }
 

@@ -240,5 +240,8 @@ int run_webserver(const RenderEnv &ren, int width, int height, int port, int dev
 void save_png_rgb8(const std::string &path, const uint8_t *rgb, uint32_t w, uint32_t h);
 std::vector<uint8_t> encode_png_rgb8(const uint8_t *rgb, uint32_t w, uint32_t h);
 std::shared_ptr<TextureRgb8> load_png_rgb8(const std::string &path);  // nullptr unless it decodes to RGB8
+std::shared_ptr<TextureRgb8> load_jpeg_rgb8(const std::vector<uint8_t> &file_bytes);  // baseline 3-component JPEG (rr_jpeg.cpp), else nullptr
+// image::open(path).ok() restricted to DynamicImage::ImageRgb8 (render.rs:165-181, :251): PNG or baseline JPEG by signature
+std::shared_ptr<TextureRgb8> load_image_rgb8(const std::string &path);
 
 }  // namespace rr

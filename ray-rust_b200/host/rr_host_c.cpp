@@ -86,9 +86,27 @@ int rrh_render_rgb8(void *h, uint8_t *out) {
 int rrh_png_roundtrip(const uint8_t *rgb, uint32_t w, uint32_t h, const char *path, uint8_t *back) {
     try {
         rr::save_png_rgb8(path, rgb, w, h);
-        auto t = rr::load_png_rgb8(path);
+        auto t = rr::load_image_rgb8(path);
         if (!t || t->width != w || t->height != h) return -2;
         memcpy(back, t->rgb8.data(), (size_t)w * h * 3);
+        return 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// image::open(path) as the texture loader sees it: 0 and the RGB8 pixels, or -2 when the file is not an RGB8 image
+// (`out` may be null to query the size only).
+int rrh_load_image(const char *path, uint32_t *w, uint32_t *h, uint8_t *out, uint64_t cap) {
+    try {
+        auto t = rr::load_image_rgb8(path);
+        if (!t) return -2;
+        *w = t->width; *h = t->height;
+        if (out) {
+            if (cap < t->rgb8.size()) return -3;
+            memcpy(out, t->rgb8.data(), t->rgb8.size());
+        }
         return 0;
     } catch (const std::exception &e) {
         g_err = e.what();

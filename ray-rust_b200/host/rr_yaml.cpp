@@ -452,7 +452,7 @@ void RenderEnv::deserialize(const std::string &s) {
             mat->pattern_angle_scale_ = as_f32(field(m, "pattern_angle_scale"));
             mat->texture_name_ = as_str(field(m, "texture_name"));
             mat->texture_filter_ = as_enum(field(m, "texture_filter"), FILTERS);
-            if (!mat->texture_name_.empty()) mat->texture_ = load_png_rgb8(mat->texture_name_);  // image::open(..).ok()
+            if (!mat->texture_name_.empty()) mat->texture_ = load_image_rgb8(mat->texture_name_);  // image::open(..).ok()
             mm[kv.first] = mat;
         }
         objs = &field(root, "objects");

@@ -27,6 +27,7 @@ def host(rr):
     lib.rrh_env_limits.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.rrh_last_error.restype = C.c_char_p
     lib.rrh_png_roundtrip.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_void_p]
+    lib.rrh_load_image.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p, C.c_uint64]
     return lib
 
 
@@ -219,6 +220,65 @@ def test_png_writer_and_reader(host, tmp_path):
     assert host.rrh_env_deserialize(h, text.replace(path2, rgba).encode()) == 0
     host.rrh_env_flatten(h, C.byref(d), C.byref(p))
     assert d.n_textures == 0   # RGBA is not ImageRgb8: silently falls back to the pattern (render.rs:251)
+    host.rrh_env_free(h)
+
+
+def _load_image(host, path):
+    w, h = C.c_uint32(), C.c_uint32()
+    rc = host.rrh_load_image(str(path).encode(), C.byref(w), C.byref(h), None, 0)
+    if rc != 0:
+        return rc
+    out = np.zeros((h.value, w.value, 3), np.uint8)
+    assert host.rrh_load_image(str(path).encode(), C.byref(w), C.byref(h), out.ctypes.data_as(C.c_void_p), out.size) == 0
+    return out
+
+
+def test_jpeg_textures_decode_like_a_conforming_decoder(host, tmp_path):
+    """image::open() loads JPEG textures too (render.rs:165-181). The host decodes baseline JPEG itself (rr_jpeg.cpp); T.81
+    leaves IDCT and chroma upsampling to the decoder within a level or so, hence the comparison with libjpeg-turbo (PIL) is
+    a tolerance, not equality: every texel within 3 levels, 99 % within 1 (4:4:4, no upsampling: within 2)."""
+    from PIL import Image
+
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[0:77, 0:101]
+    smooth = np.stack([128 + 100 * np.sin(xx / 9.0) * np.cos(yy / 13.0), 128 + 90 * np.cos(xx / 17.0 + yy / 5.0), (xx * 2 + yy) % 256], -1)
+    img = np.clip(smooth + rng.normal(0, 6, smooth.shape), 0, 255).astype(np.uint8)
+    for name, kw, tol in (("444", dict(subsampling=0), 2), ("422", dict(subsampling=1), 3), ("420", dict(subsampling=2), 3),
+                          ("420q50", dict(subsampling=2, quality=50), 3), ("opt", dict(subsampling=0, optimize=True, quality=95), 2)):
+        path = tmp_path / f"t_{name}.jpg"
+        Image.fromarray(img).save(path, "JPEG", quality=kw.pop("quality", 90), **kw)
+        ref = np.asarray(Image.open(path).convert("RGB")).astype(int)
+        got = _load_image(host, path)
+        assert isinstance(got, np.ndarray) and got.shape == ref.shape, (name, got)
+        d = np.abs(got.astype(int) - ref)
+        assert d.max() <= tol, (name, int(d.max()))
+        assert (d <= 1).mean() >= 0.99, (name, float((d <= 1).mean()))
+    # restart intervals, and sizes that are not a multiple of the MCU
+    small = img[:19, :23]
+    path = tmp_path / "rst.jpg"
+    Image.fromarray(small).save(path, "JPEG", quality=92, subsampling=2, restart_marker_blocks=1)
+    assert b"\xff\xdd" in path.read_bytes()  # DRI present
+    got, ref = _load_image(host, path), np.asarray(Image.open(path).convert("RGB")).astype(int)
+    assert np.abs(got.astype(int) - ref).max() <= 3
+    # what image::open() does not turn into ImageRgb8, or this decoder does not cover: quietly "no texture"
+    grey = tmp_path / "grey.jpg"
+    Image.fromarray(img[:, :, 0]).save(grey, "JPEG")
+    assert _load_image(host, grey) == -2           # ImageLuma8: ignored by render.rs:251
+    prog = tmp_path / "prog.jpg"
+    Image.fromarray(img).save(prog, "JPEG", progressive=True)
+    assert _load_image(host, prog) == -2           # progressive frames: outside this decoder (DESIGN.md 1, deviation 4)
+    trunc = tmp_path / "trunc.jpg"
+    trunc.write_bytes((tmp_path / "t_420.jpg").read_bytes()[:300])
+    assert _load_image(host, trunc) == -2
+    assert _load_image(host, tmp_path / "missing.jpg") == -2
+    # through the scene YAML, like a reference scene that names a .jpg texture
+    h = host.rrh_env_new(0, 8, 8, 0, 0, 0.0, 0, 0)
+    text = _serialize(host, h).replace('texture_name: bar.png', f'texture_name: {tmp_path / "t_444.jpg"}')
+    assert host.rrh_env_deserialize(h, text.encode()) == 0
+    from ray_rust_b200 import ffi
+    d, p = ffi.rr_scene_desc(), ffi.rr_frame_params()
+    host.rrh_env_flatten(h, C.byref(d), C.byref(p))
+    assert d.n_textures == 1 and (d.textures[0].width, d.textures[0].height) == (101, 77)
     host.rrh_env_free(h)
 
 

@@ -202,7 +202,10 @@ int rr_render_f32(rr_scene *scene, const rr_frame_params *params, float *out_rgb
 /* Same kernels, result left in DEVICE memory on `device` of the handle. `cuda_stream` is a
  * cudaStream_t (NULL = the handle's own stream); the call is asynchronous w.r.t. that stream when
  * a stream is given, and synchronises when NULL. Used for device-resident timing and to hand the
- * rows to a collective (NCCL gather of row bands). */
+ * rows to a collective (NCCL gather of row bands).
+ * Mind that CUDA's DEFAULT stream has the handle 0: passing it means NULL here, i.e. a blocking launch on the handle's
+ * own stream that is NOT ordered with work queued on the default stream. Callers that time or pipeline launches create a
+ * stream (cudaStreamCreate, torch.cuda.Stream()) and pass that. */
 int rr_render_rgb8_device(rr_scene *scene, const rr_frame_params *params, void *d_out,
                           size_t row_stride, void *cuda_stream);
 int rr_render_f32_device(rr_scene *scene, const rr_frame_params *params, void *d_out_rgb,

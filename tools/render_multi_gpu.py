@@ -38,7 +38,8 @@ def main():
         ren.deserialize(open(a.deserialize_file).read())
     scene = rr.DeviceScene(ren, lr)
     frame = SharedDeviceFrame(dist, rank, world, lr, a.width, a.height)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # not the default stream (handle 0 = NULL = blocking launch on the handle's own stream)
+    torch.cuda.set_stream(stream)
     ms = []
     for _ in range(a.frames):
         if world > 1:

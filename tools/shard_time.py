@@ -14,7 +14,8 @@ scene = rr.DeviceScene(ren, 0)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
 whole = ren.frame_params()
 buf = torch.empty(whole.yres * whole.xres * 3, dtype=torch.uint8, device="cuda:0")
-st = torch.cuda.current_stream()
+st = torch.cuda.Stream()  # not the default stream (handle 0 = NULL = blocking launch on the handle's own stream)
+torch.cuda.set_stream(st)
 prewarm = ren.frame_params(16, 0, 13) if os.environ.get("RR_PREWARM") else None  # a 1/13 shard: same kernel instance, other rows
 def t(p):
     ms = []

@@ -106,10 +106,12 @@ const uint8_t ZIGZAG[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 
                             30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
 // Integer 8x8 inverse DCT, 12-bit fixed-point constants, column pass then row pass, output level-shifted and clamped.
+// 64-bit intermediates: a hostile file can carry coefficients (clamped to +-2^20 by the caller) far outside what an
+// encoder produces, and the 32-bit sums of the textbook version would overflow on them.
 inline int f2f(double x) { return (int)(x * 4096 + 0.5); }
-inline uint8_t clamp8(int x) { return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); }
+inline uint8_t clamp8(long long x) { return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); }
 #define RR_IDCT_1D(s0, s1, s2, s3, s4, s5, s6, s7)                                       \
-    int t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3;                              \
+    long long t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3;                        \
     p2 = s2; p3 = s6;                                                                    \
     p1 = (p2 + p3) * f2f(0.5411961);                                                     \
     t2 = p1 + p3 * f2f(-1.847759065);                                                    \
@@ -126,13 +128,13 @@ inline uint8_t clamp8(int x) { return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x))
     p3 = p3 * f2f(-1.961570560); p4 = p4 * f2f(-0.390180644);                            \
     t3 += p1 + p4; t2 += p2 + p3; t1 += p2 + p4; t0 += p1 + p3;
 
-void idct_block(const int *in, uint8_t *out, int stride) {
-    int tmp[64];
+void idct_block(const long long *in, uint8_t *out, int stride) {
+    long long tmp[64];
     for (int i = 0; i < 8; ++i) {
-        const int *d = in + i;
-        int *v = tmp + i;
+        const long long *d = in + i;
+        long long *v = tmp + i;
         if (d[8] == 0 && d[16] == 0 && d[24] == 0 && d[32] == 0 && d[40] == 0 && d[48] == 0 && d[56] == 0) {
-            const int dc = d[0] * 4;
+            const long long dc = d[0] * 4;
             v[0] = v[8] = v[16] = v[24] = v[32] = v[40] = v[48] = v[56] = dc;
             continue;
         }
@@ -144,7 +146,7 @@ void idct_block(const int *in, uint8_t *out, int stride) {
         v[24] = (x3 + t0) >> 10; v[32] = (x3 - t0) >> 10;
     }
     for (int i = 0; i < 8; ++i) {
-        const int *v = tmp + i * 8;
+        const long long *v = tmp + i * 8;
         uint8_t *o = out + i * stride;
         RR_IDCT_1D(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7])
         x0 += 65536 + (128 << 17); x1 += 65536 + (128 << 17); x2 += 65536 + (128 << 17); x3 += 65536 + (128 << 17);
@@ -286,7 +288,9 @@ std::shared_ptr<TextureRgb8> load_jpeg_rgb8(const std::vector<uint8_t> &d) {
                 comp[c].px.assign((size_t)comp[c].bw * 8 * comp[c].bh * 8, 0);
             }
             BitReader br{&d[p + len], d.data() + d.size()};
-            int coef[64], todo = restart, next_rst = 0;
+            long long coef[64];
+            int todo = restart, next_rst = 0;
+            auto lim = [](long long v) { return v < -(1ll << 20) ? -(1ll << 20) : (v > (1ll << 20) ? (1ll << 20) : v); };
             for (int my = 0; my < mcuy; ++my)
                 for (int mx = 0; mx < mcux; ++mx) {
                     if (restart && todo == 0) {
@@ -307,8 +311,8 @@ std::shared_ptr<TextureRgb8> load_jpeg_rgb8(const std::vector<uint8_t> &d) {
                                 memset(coef, 0, sizeof coef);
                                 int t = decode_sym(br, dc[cc.td]);
                                 if (t < 0 || t > 11) return nullptr;
-                                cc.pred += t ? extend(br.get(t), t) : 0;
-                                coef[0] = cc.pred * qt[cc.tq][0];
+                                cc.pred = (int)lim((long long)cc.pred + (t ? extend(br.get(t), t) : 0));
+                                coef[0] = lim((long long)cc.pred * qt[cc.tq][0]);
                                 for (int k = 1; k < 64;) {
                                     const int rs = decode_sym(br, ac[cc.ta]);
                                     if (rs < 0) return nullptr;
@@ -320,7 +324,7 @@ std::shared_ptr<TextureRgb8> load_jpeg_rgb8(const std::vector<uint8_t> &d) {
                                     }
                                     k += r;
                                     if (k > 63) return nullptr;
-                                    coef[ZIGZAG[k]] = extend(br.get(s), s) * qt[cc.tq][ZIGZAG[k]];
+                                    coef[ZIGZAG[k]] = lim((long long)extend(br.get(s), s) * qt[cc.tq][ZIGZAG[k]]);
                                     ++k;
                                 }
                                 const size_t ox = (size_t)(mx * cc.h + bx) * 8, oy = (size_t)(my * cc.v + by) * 8;

@@ -67,13 +67,15 @@ march_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
     const int lane = threadIdx.x & 31;
     const int col = lane & 7, row = lane >> 3;
     Counters cnt = {};
+    const int rot = P.march_tile_rot < tiles_y ? P.march_tile_rot : 0;
 
     for (;;) {
         int tile = 0;
         if (lane == 0) tile = (int)atomicAdd(sig.work, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= ntiles) break;
-        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int tq = tile / tiles_x, tx = tile - tq * tiles_x;
+        const int ty = tq + rot < tiles_y ? tq + rot : tq + rot - tiles_y;  // served from the horizon rows on (FrameParams::march_tile_rot)
         const int x0 = tx << 3, ly0 = ty << 2;
         const int ix = x0 + col, ly = ly0 + row;
         const bool valid = ix < W && ly < rows;

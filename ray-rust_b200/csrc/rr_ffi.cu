@@ -74,8 +74,37 @@ struct PrimTable {
     float key[6] = {};  // xfov, yfov, cam_rot[4], compared bitwise
 };
 
+// Profile-guided tile-row order of the ray-march kernel. A march frame's time is set by its longest warp tiles and by WHEN
+// they start (1.7 % of the tiles hold ~80 % of the work, a single tile runs for up to ~2 ms); which rows
+// hold them depends on the scene and the camera. Every march launch records the longest tile of each of its tile rows
+// (RowProfile::cost, copied back asynchronously behind the kernel); the next launch of the same frame geometry on this
+// handle — the next frame of an animation, the next request of the web front-end, the next step of a benchmark — serves
+// the rows longest first (RowProfile::order, a permutation generated on the host from the last COMPLETED profile, uploaded
+// on the launch's stream in front of the kernel). Scheduling only: every tile is rendered once, with the same arithmetic.
+constexpr int RR_PROF_SLOTS = 8;       // launches of one handle whose profiles may be in flight at once
+constexpr int RR_PROF_MAX_ROWS = 4096; // tile rows (16 384 pixel rows); larger launches are not profiled
+struct ProfKey {
+    int mode, xres, yres, local_rows, row0, band_rows, band_index, band_count, band_span;
+    bool operator==(const ProfKey &o) const { return memcmp(this, &o, sizeof *this) == 0; }
+};
+struct MarchProfile {
+    std::mutex mu;
+    bool ready = false, failed = false;
+    unsigned *d_cost = nullptr, *h_cost = nullptr;  // [RR_PROF_SLOTS][RR_PROF_MAX_ROWS]; h_* page-locked
+    int *d_order = nullptr, *h_order = nullptr;
+    cudaEvent_t ev[RR_PROF_SLOTS] = {};
+    int state[RR_PROF_SLOTS] = {};  // 0 free, 1 reserved by a launch in progress, 2 copy-back queued (ev recorded)
+    ProfKey key[RR_PROF_SLOTS] = {};
+    int rows[RR_PROF_SLOTS] = {};
+    unsigned long long seq[RR_PROF_SLOTS] = {};
+    unsigned long long next_seq = 1, order_seq = 0;
+    std::vector<int> order;  // the current profile: tile rows, longest first
+    ProfKey order_key{};
+};
+
 struct rr_scene {
     int device = 0;
+    MarchProfile prof;
     rr::DevScene G{};
     rr::SceneHead H{};
     rr::LaunchInfo li{};
@@ -93,6 +122,7 @@ struct rr_scene {
     float last_ms = 0.0f;
     bool timed = false;
     bool culling = true;
+    bool profile_rows = true;    // march launches record / use the tile-row profile (RR_ROW_PROFILE=0 turns it off)
 };
 constexpr unsigned RR_SLOTS = 64;
 
@@ -181,6 +211,89 @@ int bind_prim_table(rr_scene *s, rr::FrameParams &P, cudaStream_t st) {
     return RR_OK;
 }
 
+// ---- march profile (see MarchProfile) -----------------------------------------------------------------------------
+bool prof_init(MarchProfile &m) {  // under m.mu
+    if (m.ready) return true;
+    if (m.failed) return false;
+    const size_t n = (size_t)RR_PROF_SLOTS * RR_PROF_MAX_ROWS;
+    bool ok = cudaMalloc(reinterpret_cast<void **>(&m.d_cost), n * sizeof(unsigned)) == cudaSuccess &&
+              cudaMalloc(reinterpret_cast<void **>(&m.d_order), n * sizeof(int)) == cudaSuccess &&
+              cudaHostAlloc(reinterpret_cast<void **>(&m.h_cost), n * sizeof(unsigned), cudaHostAllocDefault) == cudaSuccess &&
+              cudaHostAlloc(reinterpret_cast<void **>(&m.h_order), n * sizeof(int), cudaHostAllocDefault) == cudaSuccess;
+    for (int k = 0; ok && k < RR_PROF_SLOTS; ++k) ok = cudaEventCreateWithFlags(&m.ev[k], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); m.failed = true; return false; }  // a hint only: render without it
+    m.ready = true;
+    return true;
+}
+void prof_free(MarchProfile &m) {
+    if (m.d_cost) cudaFree(m.d_cost);
+    if (m.d_order) cudaFree(m.d_order);
+    if (m.h_cost) cudaFreeHost(m.h_cost);
+    if (m.h_order) cudaFreeHost(m.h_order);
+    for (auto &e : m.ev) if (e) cudaEventDestroy(e);
+}
+void prof_harvest(MarchProfile &m, int k) {  // under m.mu; slot k's copy-back has completed
+    m.state[k] = 0;
+    if (m.seq[k] < m.order_seq) return;  // a newer launch has already been harvested
+    const unsigned *c = m.h_cost + (size_t)k * RR_PROF_MAX_ROWS;
+    const int n = m.rows[k];
+    m.order.resize((size_t)n);
+    for (int i = 0; i < n; ++i) m.order[(size_t)i] = i;
+    std::stable_sort(m.order.begin(), m.order.end(), [c](int a, int b) { return c[a] > c[b]; });
+    m.order_key = m.key[k];
+    m.order_seq = m.seq[k];
+}
+// Before a march launch: picks a profile slot, queues (on `st`) the upload of the row order when a completed profile of this
+// geometry exists and the clearing of the slot's cost words. Returns the slot, or -1 (launch without profile).
+int prof_begin(rr_scene *s, const rr::FrameParams &P, cudaStream_t st, rr::RowProfile *out) {
+    *out = rr::RowProfile{nullptr, nullptr};
+    const int tiles_y = (P.local_rows + 3) / 4;
+    if (tiles_y < 8 || tiles_y > RR_PROF_MAX_ROWS) return -1;
+    MarchProfile &m = s->prof;
+    std::lock_guard<std::mutex> lk(m.mu);
+    if (!prof_init(m)) return -1;
+    for (int k = 0; k < RR_PROF_SLOTS; ++k)
+        if (m.state[k] == 2 && cudaEventQuery(m.ev[k]) == cudaSuccess) prof_harvest(m, k);
+    cudaGetLastError();  // (cudaErrorNotReady of the queries)
+    int slot = -1;
+    for (int k = 0; k < RR_PROF_SLOTS && slot < 0; ++k)
+        if (m.state[k] == 0) slot = k;
+    if (slot < 0) return -1;  // more launches in flight than slots: this one goes unprofiled
+    const ProfKey key{P.use_raymarching ? 1 : 0, P.xres, P.yres, P.local_rows, P.row0, P.band_rows, P.band_index, P.band_count, P.band_span};
+    unsigned *d_cost = m.d_cost + (size_t)slot * RR_PROF_MAX_ROWS;
+    if (cudaMemsetAsync(d_cost, 0, (size_t)tiles_y * sizeof(unsigned), st) != cudaSuccess) { cudaGetLastError(); return -1; }
+    out->cost = d_cost;
+    if (m.order_seq && m.order_key == key && (int)m.order.size() == tiles_y) {
+        int *h = m.h_order + (size_t)slot * RR_PROF_MAX_ROWS, *d = m.d_order + (size_t)slot * RR_PROF_MAX_ROWS;
+        memcpy(h, m.order.data(), (size_t)tiles_y * sizeof(int));
+        if (cudaMemcpyAsync(d, h, (size_t)tiles_y * sizeof(int), cudaMemcpyHostToDevice, st) == cudaSuccess) out->order = d;
+        else cudaGetLastError();
+    }
+    m.key[slot] = key;
+    m.rows[slot] = tiles_y;
+    m.seq[slot] = m.next_seq++;
+    m.state[slot] = 1;  // reserved; prof_end records the event (on failure the slot is released there)
+    return slot;
+}
+// After the launch: queue the copy-back of the cost words and the event that marks the slot complete.
+void prof_end(rr_scene *s, int slot, cudaStream_t st, bool launched) {
+    if (slot < 0) return;
+    MarchProfile &m = s->prof;
+    std::lock_guard<std::mutex> lk(m.mu);
+    bool ok = launched;
+    ok = ok && cudaMemcpyAsync(m.h_cost + (size_t)slot * RR_PROF_MAX_ROWS, m.d_cost + (size_t)slot * RR_PROF_MAX_ROWS,
+                               (size_t)m.rows[slot] * sizeof(unsigned), cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok = ok && cudaEventRecord(m.ev[slot], st) == cudaSuccess;
+    if (ok) {
+        m.state[slot] = 2;
+    } else {
+        // nothing will complete this slot's event; whatever was queued for it only touches the slot's own buffers, which
+        // stay allocated until the handle is destroyed. The slot goes back unharvested.
+        cudaGetLastError();
+        m.state[slot] = 0;
+    }
+}
+
 int launch(rr_scene *s, const rr::FrameParams &P_in, void *d_out, size_t row_stride, bool f32, rr::Counters *d_cnt,
            cudaStream_t st, unsigned *d_flag = nullptr, unsigned epoch = 0) {
     rr::FrameParams P = P_in;
@@ -196,8 +309,15 @@ int launch(rr_scene *s, const rr::FrameParams &P_in, void *d_out, size_t row_str
     unsigned *slot = s->d_work + 4 * (s->launch_seq.fetch_add(1u, std::memory_order_relaxed) % RR_SLOTS);
     const rr::Signal sig{slot, slot + 1, d_flag, epoch};
     const bool fused = d_flag && P.xres > 0 && P.local_rows > 0;
-    cudaError_t e = P.use_raymarching ? rr::launch_march(s->G, s->H, P, d_out, row_stride, f32, d_cnt, sig, st, s->li, s->culling)
-                                      : rr::launch_trace(s->G, s->H, P, d_out, row_stride, f32, d_cnt, st, s->li, s->culling, sig);
+    cudaError_t e;
+    if (P.use_raymarching) {
+        rr::RowProfile prof{nullptr, nullptr};
+        const int pslot = (P.xres > 0 && P.local_rows > 0 && s->profile_rows) ? prof_begin(s, P, st, &prof) : -1;
+        e = rr::launch_march(s->G, s->H, P, d_out, row_stride, f32, d_cnt, sig, st, s->li, s->culling, prof);
+        prof_end(s, pslot, st, e == cudaSuccess);
+    } else {
+        e = rr::launch_trace(s->G, s->H, P, d_out, row_stride, f32, d_cnt, st, s->li, s->culling, sig);
+    }
     if (e == cudaSuccess && d_flag && !fused) e = rr::launch_signal(sig, st);
     if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
     return RR_OK;
@@ -352,7 +472,9 @@ int rr_scene_destroy(rr_scene *s) {
         if (l.stream) cudaStreamSynchronize(l.stream);
         if (l.copy_stream) cudaStreamSynchronize(l.copy_stream);
     }
+    cudaDeviceSynchronize();  // launches on caller streams may still be writing the profile buffers
     for (void *p : s->allocs) cudaFree(p);
+    prof_free(s->prof);
     for (PrimTable &t : s->ptabs) if (t.d) cudaFree(t.d);
     for (Lane &l : s->lanes) {
         if (l.d_out) cudaFree(l.d_out);
@@ -399,6 +521,10 @@ int rr_scene_create(const rr_scene_desc *desc, int device, rr_scene **out) {
     rr_scene *s = new (std::nothrow) rr_scene();
     if (!s) return fail(RR_ERR_OOM, "host allocation failed");
     s->device = device;
+    {
+        const char *e = getenv("RR_ROW_PROFILE");
+        s->profile_rows = !(e && atoi(e) == 0);
+    }
     int rc = RR_OK;
     auto bail = [&](int code) { rr_scene_destroy(s); return code; };
 

@@ -14,6 +14,14 @@ struct LaunchInfo {
     size_t smem_optin;  // max opt-in dynamic shared memory per block
 };
 
+// Tile-row order of a launch (a permutation of its (local_rows + 3) / 4 tile rows of 8x4 warp tiles, or nullptr) and where
+// the kernel records the longest tile of every tile row (zeroed by the caller, or nullptr): see MarchProfile in rr_ffi.cu.
+// Ray-march kernel only: the same order on the BVH instances of the ray-trace kernel measured neutral on one GPU (1.790 vs
+// 1.786 ms) and 14 % SLOWER on band-sharded frames (4 GPUs: 0.597 -> 0.679 ms, profiles/r3l_bench_n4_rowprofile_bvh.json).
+struct RowProfile {
+    const int *order;
+    unsigned *cost;
+};
 // Ray-trace mode. d_out: RGB8 (row_stride bytes per row) or, when f32_out, packed float rgb.
 // d_cnt != nullptr selects the instrumented instantiation.
 cudaError_t launch_trace(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
@@ -21,7 +29,8 @@ cudaError_t launch_trace(const DevScene &G, const SceneHead &H, const FrameParam
 // Ray-march mode (same contract). sig.work / sig.done: this launch's tile-queue word and block counter (both zero at
 // launch; the last block resets them), sig.flag: optional completion word, as for the trace kernel.
 cudaError_t launch_march(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride, bool f32_out,
-                         Counters *d_cnt, const Signal &sig, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh = true);
+                         Counters *d_cnt, const Signal &sig, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh = true,
+                         const RowProfile &prof = RowProfile{nullptr, nullptr});
 // Fills the primary-ray tables of a frame (FrameParams::ptab layout: xres column entries, then yres row entries).
 cudaError_t launch_prim_table(const FrameParams &P, float4 *d_tab, cudaStream_t stream);
 // Row-band un-interleave (multi-GPU gather epilogue).

@@ -57,7 +57,7 @@ __device__ __forceinline__ MarchView stage_march(const DevScene &G, float4 *smem
 template <bool COUNT, bool F32OUT, bool STAGE, int GLOW, bool MBVH>
 __global__ void __launch_bounds__(MARCH_THREADS)
 march_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHead H, const __grid_constant__ FrameParams P,
-             void *__restrict__ out, size_t row_stride, Counters *gcnt, int fast_store, const Signal sig) {
+             void *__restrict__ out, size_t row_stride, Counters *gcnt, int fast_store, const Signal sig, const RowProfile prof) {
     extern __shared__ float4 rr_smem[];
     const MarchView S = stage_march(G, rr_smem, STAGE);
 
@@ -75,7 +75,10 @@ march_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= ntiles) break;
         const int tq = tile / tiles_x, tx = tile - tq * tiles_x;
-        const int ty = tq + rot < tiles_y ? tq + rot : tq + rot - tiles_y;  // served from the horizon rows on (FrameParams::march_tile_rot)
+        // tile ROW order: the handle's profile of an earlier launch of this frame geometry (longest rows first), else from
+        // the horizon rows on (FrameParams::march_tile_rot)
+        const int ty = prof.order ? __ldg(&prof.order[tq]) : (tq + rot < tiles_y ? tq + rot : tq + rot - tiles_y);
+        const long long t_begin = prof.cost ? clock64() : 0ll;
         const int x0 = tx << 3, ly0 = ty << 2;
         const int ix = x0 + col, ly = ly0 + row;
         const bool valid = ix < W && ly < rows;
@@ -90,6 +93,10 @@ march_kernel(const __grid_constant__ DevScene G, const __grid_constant__ SceneHe
             const unsigned rgb = quantize(c.x) | (quantize(c.y) << 8) | (quantize(c.z) << 16);
             store_tile_rgb8(reinterpret_cast<uint8_t *>(out), row_stride, x0, ly0, W, rows, rgb, fast_store != 0,
                             P.placed ? local_to_image_row(P, ly) : ly);
+        }
+        if (prof.cost && lane == 0) {  // the row's longest tile, in units of 64 clocks
+            const long long d = (clock64() - t_begin) >> 6;
+            atomicMax(&prof.cost[ty], (unsigned)(d < 0 ? 0 : (d > 0xffffffffll ? 0xffffffffll : d)));
         }
     }
     if (COUNT) flush_counters(cnt, gcnt);
@@ -107,7 +114,7 @@ static size_t march_smem_bytes(const DevScene &G) {
 
 template <bool COUNT, bool F32OUT, bool STAGE, int GLOW, bool MBVH = false>
 static cudaError_t launch_one(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
-                              Counters *d_cnt, const Signal &sig, cudaStream_t stream, const LaunchInfo &li, size_t smem) {
+                              Counters *d_cnt, const Signal &sig, cudaStream_t stream, const LaunchInfo &li, size_t smem, const RowProfile &prof) {
     auto kern = march_kernel<COUNT, F32OUT, STAGE, GLOW, MBVH>;
     cudaError_t e;
     if (smem > 48 * 1024) {
@@ -124,13 +131,13 @@ static cudaError_t launch_one(const DevScene &G, const SceneHead &H, const Frame
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     const int fast = (!F32OUT && (P.xres % 8 == 0) && (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0)) ? 1 : 0;
-    kern<<<(unsigned)grid, MARCH_THREADS, smem, stream>>>(G, H, P, d_out, row_stride, d_cnt, fast, sig);
+    kern<<<(unsigned)grid, MARCH_THREADS, smem, stream>>>(G, H, P, d_out, row_stride, d_cnt, fast, sig, prof);
     return cudaGetLastError();
 }
 
 template <bool COUNT, bool F32OUT>
 static cudaError_t launch_two(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
-                              Counters *d_cnt, const Signal &sig, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh) {
+                              Counters *d_cnt, const Signal &sig, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh, const RowProfile &prof) {
     size_t smem = march_smem_bytes(G);
     const bool stage = smem <= li.smem_optin / 2;
     if (!stage) smem = 0;
@@ -140,26 +147,26 @@ static cudaError_t launch_two(const DevScene &G, const SceneHead &H, const Frame
     // Large scenes: the sphere scan goes through the BVH (rr_march.cuh, MBVH); nothing is staged (floor tails and BVH are
     // read through L1). Inline glow keeps the linear scan.
     if (allow_bvh && G.n_bvh_nodes > 0 && glow != 2) {
-        if (glow == 0) return launch_one<COUNT, F32OUT, false, 0, true>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, 0);
-        return launch_one<COUNT, F32OUT, false, 1, true>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, 0);
+        if (glow == 0) return launch_one<COUNT, F32OUT, false, 0, true>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, 0, prof);
+        return launch_one<COUNT, F32OUT, false, 1, true>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, 0, prof);
     }
     if (stage) {
-        if (glow == 0) return launch_one<COUNT, F32OUT, true, 0>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem);
-        if (glow == 1) return launch_one<COUNT, F32OUT, true, 1>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem);
-        return launch_one<COUNT, F32OUT, true, 2>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem);
+        if (glow == 0) return launch_one<COUNT, F32OUT, true, 0>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem, prof);
+        if (glow == 1) return launch_one<COUNT, F32OUT, true, 1>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem, prof);
+        return launch_one<COUNT, F32OUT, true, 2>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem, prof);
     }
-    if (glow == 0) return launch_one<COUNT, F32OUT, false, 0>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem);
-    if (glow == 1) return launch_one<COUNT, F32OUT, false, 1>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem);
-    return launch_one<COUNT, F32OUT, false, 2>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem);
+    if (glow == 0) return launch_one<COUNT, F32OUT, false, 0>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem, prof);
+    if (glow == 1) return launch_one<COUNT, F32OUT, false, 1>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem, prof);
+    return launch_one<COUNT, F32OUT, false, 2>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, smem, prof);
 }
 
 cudaError_t launch_march(const DevScene &G, const SceneHead &H, const FrameParams &P, void *d_out, size_t row_stride,
-                         bool f32_out, Counters *d_cnt, const Signal &sig, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh) {
+                         bool f32_out, Counters *d_cnt, const Signal &sig, cudaStream_t stream, const LaunchInfo &li, bool allow_bvh, const RowProfile &prof) {
     if (P.xres <= 0 || P.local_rows <= 0) return cudaSuccess;
-    if (d_cnt) return f32_out ? launch_two<true, true>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, allow_bvh)
-                              : launch_two<true, false>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, allow_bvh);
-    return f32_out ? launch_two<false, true>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, allow_bvh)
-                   : launch_two<false, false>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, allow_bvh);
+    if (d_cnt) return f32_out ? launch_two<true, true>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, allow_bvh, prof)
+                              : launch_two<true, false>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, allow_bvh, prof);
+    return f32_out ? launch_two<false, true>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, allow_bvh, prof)
+                   : launch_two<false, false>(G, H, P, d_out, row_stride, d_cnt, sig, stream, li, allow_bvh, prof);
 }
 
 }  // namespace rr

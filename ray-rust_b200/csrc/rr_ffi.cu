@@ -258,7 +258,16 @@ int prof_begin(rr_scene *s, const rr::FrameParams &P, cudaStream_t st, rr::RowPr
     int slot = -1;
     for (int k = 0; k < RR_PROF_SLOTS && slot < 0; ++k)
         if (m.state[k] == 0) slot = k;
-    if (slot < 0) return -1;  // more launches in flight than slots: this one goes unprofiled
+    if (slot < 0) {
+        // RR_PROF_SLOTS launches of this handle are in flight (a caller queueing frames far ahead on its stream): wait for
+        // the oldest one, like rr_render_rgb8_async waits for a lane. Bounds the run-ahead to a few frames of GPU work.
+        int oldest = -1;
+        for (int k = 0; k < RR_PROF_SLOTS; ++k)
+            if (m.state[k] == 2 && (oldest < 0 || m.seq[k] < m.seq[oldest])) oldest = k;
+        if (oldest < 0 || cudaEventSynchronize(m.ev[oldest]) != cudaSuccess) { cudaGetLastError(); return -1; }
+        prof_harvest(m, oldest);
+        slot = oldest;
+    }
     const ProfKey key{P.use_raymarching ? 1 : 0, P.xres, P.yres, P.local_rows, P.row0, P.band_rows, P.band_index, P.band_count, P.band_span};
     unsigned *d_cost = m.d_cost + (size_t)slot * RR_PROF_MAX_ROWS;
     if (cudaMemsetAsync(d_cost, 0, (size_t)tiles_y * sizeof(unsigned), st) != cudaSuccess) { cudaGetLastError(); return -1; }

@@ -173,3 +173,10 @@ extern "C" long long hostsim_fmod_2pi_mismatches(float lo, float hi, float *firs
     }
     return bad;
 }
+
+// the ray-march kernel's tile-row rotation (FrameParams::march_tile_rot, a host-side scheduling hint)
+extern "C" int hostsim_march_tile_rot(const rr_scene_desc *desc, const rr_frame_params *params) {
+    Flat f;
+    flatten(desc, f);
+    return to_dev(params, f.H).march_tile_rot;
+}

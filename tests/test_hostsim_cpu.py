@@ -141,3 +141,25 @@ def test_fmod_2pi_is_fmodf(hostsim):
     bad = C.c_float(0)
     for lo, hi in ((1.0, 1024.0), (1e-30, 1e-29), (4000.0, 4200.0), (0.001, 0.002)):
         assert lib.hostsim_fmod_2pi_mismatches(lo, hi, C.byref(bad)) == 0, bad.value
+
+
+def test_march_tile_rotation_hint(rr, hostsim):
+    """The ray-march kernel serves its tile rows from the floor's horizon on (FrameParams::march_tile_rot, csrc/rr_device.cuh):
+    a host-side scheduling hint. The built-in camera looks along the floor, so the horizon is the middle row; trace-mode
+    frames keep image order (band shards too: the C ABI's to_dev, exercised on the GPU box)."""
+    lib = C.CDLL(os.path.join(HS, "libhostsim.so"))  # (built by the hostsim fixture)
+
+    def rot(ren, p=None):
+        flat = ren.flatten()
+        p = p or ren.frame_params()
+        return lib.hostsim_march_tile_rot(C.byref(flat.desc), C.byref(p))
+
+    lib.hostsim_march_tile_rot.argtypes = [C.POINTER(rr.ffi.rr_scene_desc), C.POINTER(rr.ffi.rr_frame_params)]
+    march = rr.default_scene(3840, 2160, use_raymarching=True, glow_effect=1.0)
+    assert rot(march) == 2160 // 2 // 4 - 2
+    assert rot(rr.default_scene(640, 480, use_raymarching=True)) == 480 // 2 // 4 - 2
+    assert rot(rr.default_scene(3840, 2160)) == 0                       # ray-trace mode
+    up = rr.default_scene(640, 480, use_raymarching=True)
+    up.camera.rotation = rr.scene.Quat.from_pyr((np.float32(0.0), np.float32(0.0), np.float32(0.0)))  # looking straight up/down the axis: no horizon row
+    r = rot(up)
+    assert 0 <= r < 480 // 4

@@ -2,9 +2,10 @@
 //
 // The reference loads a material's texture with image::open(..) (render.rs:165-181, image 0.24.2 -> jpeg-decoder 0.2.6) and uses
 // it only when the result is DynamicImage::ImageRgb8 (render.rs:251). A three-component YCbCr JPEG decodes to exactly that,
-// a grey-scale one to ImageLuma8 (ignored by the path). This file covers what such a texture file normally is: sequential
-// Huffman-coded DCT frames (SOF0 / SOF1, 8 bits per sample), 1..4 samples per MCU axis, restart intervals, JFIF YCbCr or Adobe RGB.
-// Progressive, arithmetic-coded, lossless and 12-bit files return nullptr = "not an RGB8 image", like every other failed load.
+// a grey-scale one to ImageLuma8 (ignored by the path). This file covers what such a texture file normally is: Huffman-coded
+// DCT frames, sequential (SOF0 / SOF1) or progressive (SOF2: spectral selection and successive approximation, T.81 annex G),
+// 8 bits per sample, 1..4 samples per MCU axis, restart intervals, JFIF YCbCr or Adobe RGB.
+// Arithmetic-coded, lossless, hierarchical and 12-bit files return nullptr = "not an RGB8 image", like every other failed load.
 //
 // Arithmetic follows ITU-T T.81 with the constants of the public-domain integer IDCT (12-bit fixed point, the one jpeg-decoder's
 // idct.rs is also derived from), triangle-filter chroma upsampling for 2x1 and 2x2 subsampling (replication otherwise) and
@@ -34,6 +35,8 @@ struct Comp {
     int bw = 0, bh = 0;  // blocks per row / column (padded to whole MCUs)
     int pred = 0;
     std::vector<uint8_t> px;  // decoded samples, (bw*8) x (bh*8)
+    std::vector<int> coef;    // progressive frames: the coefficients of all blocks (natural order), refined scan by scan
+    int aw = 0, ah = 0;       // blocks that hold image samples (a non-interleaved scan visits only these)
 };
 
 struct BitReader {
@@ -157,6 +160,81 @@ void idct_block(const long long *in, uint8_t *out, int stride) {
     }
 }
 
+// ---- progressive scans (T.81 annex G) ----
+inline int clampi(long long v) { return (int)(v < -(1ll << 28) ? -(1ll << 28) : (v > (1ll << 28) ? (1ll << 28) : v)); }
+bool prog_dc(BitReader &br, Comp &c, int *blk, const Huff &h, int Ah, int Al) {
+    if (Ah == 0) {
+        const int t = decode_sym(br, h);
+        if (t < 0 || t > 11) return false;
+        c.pred = clampi((long long)c.pred + (t ? extend(br.get(t), t) : 0));
+        blk[0] = clampi((long long)c.pred * (1 << Al));
+    } else if (br.get(1)) {
+        blk[0] = clampi((long long)blk[0] + (1 << Al));
+    }
+    return true;
+}
+bool prog_ac(BitReader &br, int *blk, const Huff &h, int Ss, int Se, int Ah, int Al, int &eobrun) {
+    if (Ah == 0) {  // first pass over this band
+        if (eobrun) { --eobrun; return true; }
+        int k = Ss;
+        do {
+            const int rs = decode_sym(br, h);
+            if (rs < 0) return false;
+            const int r = rs >> 4, sz = rs & 15;
+            if (sz == 0) {
+                if (r < 15) {
+                    eobrun = (1 << r) + (r ? br.get(r) : 0) - 1;
+                    break;
+                }
+                k += 16;
+            } else {
+                k += r;
+                if (k > Se) return false;
+                blk[ZIGZAG[k++]] = extend(br.get(sz), sz) * (1 << Al);
+            }
+        } while (k <= Se);
+        return true;
+    }
+    // refinement: one more bit for the coefficients that are already non-zero, new +-1 coefficients in between
+    const int bit = 1 << Al;
+    auto refine = [&](int &v) {
+        if (br.get(1) && (v & bit) == 0) v = clampi((long long)v + (v > 0 ? bit : -bit));
+    };
+    if (eobrun) {
+        --eobrun;
+        for (int k = Ss; k <= Se; ++k) {
+            int &v = blk[ZIGZAG[k]];
+            if (v != 0) refine(v);
+        }
+        return true;
+    }
+    int k = Ss;
+    do {
+        const int rs = decode_sym(br, h);
+        if (rs < 0) return false;
+        int r = rs >> 4, sz = rs & 15, val = 0;
+        if (sz == 0) {
+            if (r < 15) {
+                eobrun = (1 << r) - 1 + (r ? br.get(r) : 0);
+                r = 64;  // run to the end of the band, refining only
+            }
+        } else {
+            if (sz != 1) return false;
+            val = br.get(1) ? bit : -bit;
+        }
+        while (k <= Se) {
+            int &v = blk[ZIGZAG[k++]];
+            if (v != 0) {
+                refine(v);
+            } else {
+                if (r == 0) { v = val; break; }
+                --r;
+            }
+        }
+    } while (k <= Se);
+    return true;
+}
+
 inline unsigned be16(const uint8_t *p) { return ((unsigned)p[0] << 8) | p[1]; }
 
 // one output row of `w` samples from a component plane, upsampled to full resolution
@@ -164,11 +242,12 @@ void upsample_row(const Comp &c, int hmax, int vmax, int y, int w, uint8_t *out)
     const int sw = c.bw * 8, sh = c.bh * 8;
     const int hs = hmax / c.h, vs = vmax / c.v;
     const int cw = (w + hs - 1) / hs;  // meaningful source samples in a row
-    if (hs == 1 && vs == 1) {
+    const bool whole = hmax % c.h == 0 && vmax % c.v == 0;  // (hostile headers may carry ratios like 4:3)
+    if (whole && hs == 1 && vs == 1) {
         memcpy(out, &c.px[(size_t)y * sw], (size_t)w);
         return;
     }
-    if ((hs == 2 && (vs == 1 || vs == 2)) && hmax % c.h == 0 && vmax % c.v == 0) {
+    if (whole && hs == 2 && (vs == 1 || vs == 2)) {
         // triangle filter: 3/4 nearer + 1/4 farther sample per axis (vertical blend first for 2x2), rounding as libjpeg's
         // "fancy" upsampling does: +8 >> 4 on even and +7 >> 4 on odd outputs for 2x2, +1 / +2 >> 2 for 2x1
         const uint8_t *near_row, *far_row = nullptr;
@@ -198,7 +277,10 @@ void upsample_row(const Comp &c, int hmax, int vmax, int y, int w, uint8_t *out)
     // any other ratio: sample replication
     const int sy = (int)((long long)y * c.v / vmax);
     const uint8_t *row = &c.px[(size_t)(sy < sh ? sy : sh - 1) * sw];
-    for (int x = 0; x < w; ++x) out[x] = row[(int)((long long)x * c.h / hmax)];
+    for (int x = 0; x < w; ++x) {
+        const int sx = (int)((long long)x * c.h / hmax);
+        out[x] = row[sx < sw ? sx : sw - 1];
+    }
 }
 
 }  // namespace
@@ -209,9 +291,68 @@ std::shared_ptr<TextureRgb8> load_jpeg_rgb8(const std::vector<uint8_t> &d) {
     bool qt_ok[4] = {false, false, false, false};
     Huff dc[4], ac[4];
     Comp comp[3];
-    int ncomp = 0, W = 0, H = 0, hmax = 1, vmax = 1, restart = 0;
-    bool have_frame = false, adobe = false;
+    int ncomp = 0, W = 0, H = 0, hmax = 1, vmax = 1, restart = 0, mcux = 0, mcuy = 0, scans = 0;
+    bool have_frame = false, progressive = false, adobe = false;
     int adobe_transform = -1;
+    auto lim = [](long long v) { return v < -(1ll << 20) ? -(1ll << 20) : (v > (1ll << 20) ? (1ll << 20) : v); };
+
+    // planes -> RGB8 (upsampling + colour conversion)
+    auto assemble = [&]() {
+        auto tex = std::make_shared<TextureRgb8>();
+        tex->width = (uint32_t)W; tex->height = (uint32_t)H;
+        tex->rgb8.resize((size_t)W * H * 3);
+        // JFIF: YCbCr. Adobe marker with transform 0: the three components ARE R, G, B.
+        const bool is_rgb = adobe && adobe_transform == 0;
+        std::vector<uint8_t> r0((size_t)W), r1((size_t)W), r2((size_t)W);
+        for (int y = 0; y < H; ++y) {
+            upsample_row(comp[0], hmax, vmax, y, W, r0.data());
+            upsample_row(comp[1], hmax, vmax, y, W, r1.data());
+            upsample_row(comp[2], hmax, vmax, y, W, r2.data());
+            uint8_t *o = &tex->rgb8[(size_t)y * W * 3];
+            for (int x = 0; x < W; ++x) {
+                if (is_rgb) { o[3 * x] = r0[x]; o[3 * x + 1] = r1[x]; o[3 * x + 2] = r2[x]; continue; }
+                // BT.601 full range, 16-bit fixed point with rounding (ITU-T T.871)
+                const int Y = r0[x] << 16, cb = r1[x] - 128, cr = r2[x] - 128;
+                o[3 * x] = clamp8((Y + 91881 * cr + 32768) >> 16);
+                o[3 * x + 1] = clamp8((Y - 22554 * cb - 46802 * cr + 32768) >> 16);
+                o[3 * x + 2] = clamp8((Y + 116130 * cb + 32768) >> 16);
+            }
+        }
+        return tex;
+    };
+    // progressive frames: all scans are in, dequantise and transform every block
+    auto finish_progressive = [&]() -> std::shared_ptr<TextureRgb8> {
+        long long blk[64];
+        for (int c = 0; c < ncomp; ++c) {
+            Comp &cc = comp[c];
+            if (!qt_ok[cc.tq]) return nullptr;
+            for (int by = 0; by < cc.bh; ++by)
+                for (int bx = 0; bx < cc.bw; ++bx) {
+                    const int *src = &cc.coef[((size_t)by * cc.bw + bx) * 64];
+                    for (int k = 0; k < 64; ++k) blk[k] = lim((long long)src[k] * qt[cc.tq][k]);
+                    idct_block(blk, &cc.px[(size_t)by * 8 * cc.bw * 8 + (size_t)bx * 8], cc.bw * 8);
+                }
+        }
+        return assemble();
+    };
+    // entropy-coded segment ends at the next marker that is not a restart marker
+    auto next_marker = [&](const uint8_t *from) {
+        const uint8_t *q = from, *end = d.data() + d.size();
+        while (q + 1 < end && !(q[0] == 0xFF && q[1] != 0x00 && q[1] != 0xFF && !(q[1] >= 0xD0 && q[1] <= 0xD7))) ++q;
+        return (size_t)(q - d.data());
+    };
+    // RSTn between restart intervals: byte-align and step over it
+    auto take_restart = [&](BitReader &br, int &next_rst) {
+        br.reset();
+        const uint8_t *q = br.p;
+        while (q + 1 < br.end && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) ++q;
+        if (q + 1 >= br.end || q[1] != 0xD0 + next_rst) return false;
+        br.p = q + 2;
+        next_rst = (next_rst + 1) & 7;
+        for (int c = 0; c < ncomp; ++c) comp[c].pred = 0;
+        return true;
+    };
+
     size_t p = 2;
     while (p + 4 <= d.size()) {
         if (d[p] != 0xFF) { ++p; continue; }
@@ -247,8 +388,9 @@ std::shared_ptr<TextureRgb8> load_jpeg_rgb8(const std::vector<uint8_t> &d) {
                 if (!build_huff(tc ? ac[th] : dc[th], &b[i + 1], &b[i + 17], total)) return nullptr;
                 i += 17 + (size_t)total;
             }
-        } else if (m == 0xC0 || m == 0xC1) {  // SOF0 / SOF1: sequential, Huffman
+        } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {  // SOF0 / SOF1: sequential, SOF2: progressive; Huffman
             if (have_frame || n < 6 || b[0] != 8) return nullptr;
+            progressive = m == 0xC2;
             H = (int)be16(&b[1]); W = (int)be16(&b[3]); ncomp = b[5];
             if (W <= 0 || H <= 0) return nullptr;
             if (ncomp != 3) return nullptr;  // 1 component = ImageLuma8 (not Rgb8), 4 = CMYK: both ignored by the path
@@ -261,17 +403,84 @@ std::shared_ptr<TextureRgb8> load_jpeg_rgb8(const std::vector<uint8_t> &d) {
                 hmax = comp[c].h > hmax ? comp[c].h : hmax;
                 vmax = comp[c].v > vmax ? comp[c].v : vmax;
             }
-            // untrusted header: refuse absurd sizes before allocating (at least ~1 bit per 8x8 block must follow)
+            // untrusted header: refuse absurd sizes before allocating (at least ~1 bit per 8x8 block must follow; a
+            // progressive frame keeps all its coefficients in memory, 4 bytes each)
             const unsigned long long blocks = ((unsigned long long)W + 7) / 8 * (((unsigned long long)H + 7) / 8);
-            if ((unsigned long long)W * H > (1ull << 28) || blocks / 8 > d.size()) return nullptr;
+            if ((unsigned long long)W * H > (progressive ? 1ull << 25 : 1ull << 28) || blocks / 8 > d.size()) return nullptr;
+            mcux = (W + 8 * hmax - 1) / (8 * hmax); mcuy = (H + 8 * vmax - 1) / (8 * vmax);
+            for (int c = 0; c < ncomp; ++c) {
+                Comp &cc = comp[c];
+                cc.bw = mcux * cc.h; cc.bh = mcuy * cc.v; cc.pred = 0;
+                cc.aw = (int)((((long long)W * cc.h + hmax - 1) / hmax + 7) / 8);
+                cc.ah = (int)((((long long)H * cc.v + vmax - 1) / vmax + 7) / 8);
+                cc.px.assign((size_t)cc.bw * 8 * cc.bh * 8, 0);
+                if (progressive) cc.coef.assign((size_t)cc.bw * cc.bh * 64, 0);
+            }
             have_frame = true;
-        } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
-            return nullptr;  // progressive / lossless / arithmetic / differential frames
+        } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+            return nullptr;  // lossless / arithmetic / differential frames
         } else if (m == 0xDD) {
             if (n < 2) return nullptr;
             restart = (int)be16(b);
         } else if (m == 0xEE) {
             if (n >= 12 && memcmp(b, "Adobe", 5) == 0) { adobe = true; adobe_transform = b[11]; }
+        } else if (m == 0xDA && progressive) {  // one of the scans of a progressive frame
+            if (!have_frame || n < 1) return nullptr;
+            const int ns = b[0];
+            if (ns < 1 || ns > ncomp || n < 1 + 2 * (size_t)ns + 3) return nullptr;
+            int sc[3];
+            for (int s2 = 0; s2 < ns; ++s2) {
+                const int cid = b[1 + 2 * s2];
+                int c = -1;
+                for (int k = 0; k < ncomp; ++k) if (comp[k].id == cid) c = k;
+                if (c < 0 || (s2 > 0 && c <= sc[s2 - 1])) return nullptr;
+                sc[s2] = c;
+                comp[c].td = b[2 + 2 * s2] >> 4; comp[c].ta = b[2 + 2 * s2] & 15;
+                if (comp[c].td > 3 || comp[c].ta > 3) return nullptr;
+            }
+            const int Ss = b[1 + 2 * ns], Se = b[2 + 2 * ns], Ah = b[3 + 2 * ns] >> 4, Al = b[3 + 2 * ns] & 15;
+            if (Ss > Se || Se > 63 || Ah > 13 || Al > 13 || (Ss == 0 && Se != 0) || (Ss > 0 && ns != 1)) return nullptr;
+            const bool is_dc = Ss == 0;
+            for (int s2 = 0; s2 < ns; ++s2) {
+                const Comp &cc = comp[sc[s2]];
+                if (is_dc ? (Ah == 0 && !dc[cc.td].ok) : !ac[cc.ta].ok) return nullptr;
+            }
+            BitReader br{&d[p + len], d.data() + d.size()};
+            int todo = restart, next_rst = 0, eobrun = 0;
+            for (int c = 0; c < ncomp; ++c) comp[c].pred = 0;
+            bool ok = true;
+            if (ns == 1) {  // non-interleaved: the component's own blocks in raster order
+                Comp &cc = comp[sc[0]];
+                for (int by = 0; ok && by < cc.ah; ++by)
+                    for (int bx = 0; ok && bx < cc.aw; ++bx) {
+                        if (restart && todo == 0) {
+                            if (!take_restart(br, next_rst)) return nullptr;
+                            todo = restart; eobrun = 0;
+                        }
+                        int *blk = &cc.coef[((size_t)by * cc.bw + bx) * 64];
+                        ok = is_dc ? prog_dc(br, cc, blk, dc[cc.td], Ah, Al) : prog_ac(br, blk, ac[cc.ta], Ss, Se, Ah, Al, eobrun);
+                        if (restart) --todo;
+                    }
+            } else {        // interleaved DC scan: MCU order
+                for (int my = 0; ok && my < mcuy; ++my)
+                    for (int mx = 0; ok && mx < mcux; ++mx) {
+                        if (restart && todo == 0) {
+                            if (!take_restart(br, next_rst)) return nullptr;
+                            todo = restart;
+                        }
+                        for (int s2 = 0; ok && s2 < ns; ++s2) {
+                            Comp &cc = comp[sc[s2]];
+                            for (int by = 0; ok && by < cc.v; ++by)
+                                for (int bx = 0; ok && bx < cc.h; ++bx)
+                                    ok = prog_dc(br, cc, &cc.coef[((size_t)(my * cc.v + by) * cc.bw + (mx * cc.h + bx)) * 64], dc[cc.td], Ah, Al);
+                        }
+                        if (restart) --todo;
+                    }
+            }
+            if (!ok) return nullptr;
+            ++scans;
+            p = next_marker(br.p);
+            continue;
         } else if (m == 0xDA) {  // SOS: the one scan of a sequential frame (interleaved)
             if (!have_frame || n < 1 || b[0] != ncomp || n < 1 + 2 * (size_t)ncomp + 3) return nullptr;
             for (int s = 0; s < ncomp; ++s) {
@@ -282,27 +491,15 @@ std::shared_ptr<TextureRgb8> load_jpeg_rgb8(const std::vector<uint8_t> &d) {
                 comp[c].td = b[2 + 2 * s] >> 4; comp[c].ta = b[2 + 2 * s] & 15;
                 if (comp[c].td > 3 || comp[c].ta > 3 || !dc[comp[c].td].ok || !ac[comp[c].ta].ok || !qt_ok[comp[c].tq]) return nullptr;
             }
-            const int mcux = (W + 8 * hmax - 1) / (8 * hmax), mcuy = (H + 8 * vmax - 1) / (8 * vmax);
-            for (int c = 0; c < ncomp; ++c) {
-                comp[c].bw = mcux * comp[c].h; comp[c].bh = mcuy * comp[c].v; comp[c].pred = 0;
-                comp[c].px.assign((size_t)comp[c].bw * 8 * comp[c].bh * 8, 0);
-            }
+            for (int c = 0; c < ncomp; ++c) comp[c].pred = 0;
             BitReader br{&d[p + len], d.data() + d.size()};
             long long coef[64];
             int todo = restart, next_rst = 0;
-            auto lim = [](long long v) { return v < -(1ll << 20) ? -(1ll << 20) : (v > (1ll << 20) ? (1ll << 20) : v); };
             for (int my = 0; my < mcuy; ++my)
                 for (int mx = 0; mx < mcux; ++mx) {
                     if (restart && todo == 0) {
-                        // byte-align, expect RSTn
-                        br.reset();
-                        const uint8_t *q = br.p;
-                        while (q + 1 < br.end && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) ++q;
-                        if (q + 1 >= br.end || q[1] != 0xD0 + next_rst) return nullptr;
-                        br.p = q + 2;
-                        next_rst = (next_rst + 1) & 7;
+                        if (!take_restart(br, next_rst)) return nullptr;
                         todo = restart;
-                        for (int c = 0; c < ncomp; ++c) comp[c].pred = 0;
                     }
                     for (int c = 0; c < ncomp; ++c) {
                         Comp &cc = comp[c];
@@ -333,31 +530,11 @@ std::shared_ptr<TextureRgb8> load_jpeg_rgb8(const std::vector<uint8_t> &d) {
                     }
                     if (restart) --todo;
                 }
-            // ---- assemble RGB8 ----
-            auto tex = std::make_shared<TextureRgb8>();
-            tex->width = (uint32_t)W; tex->height = (uint32_t)H;
-            tex->rgb8.resize((size_t)W * H * 3);
-            // JFIF: YCbCr. Adobe marker with transform 0: the three components ARE R, G, B.
-            const bool is_rgb = adobe && adobe_transform == 0;
-            std::vector<uint8_t> r0((size_t)W), r1((size_t)W), r2((size_t)W);
-            for (int y = 0; y < H; ++y) {
-                upsample_row(comp[0], hmax, vmax, y, W, r0.data());
-                upsample_row(comp[1], hmax, vmax, y, W, r1.data());
-                upsample_row(comp[2], hmax, vmax, y, W, r2.data());
-                uint8_t *o = &tex->rgb8[(size_t)y * W * 3];
-                for (int x = 0; x < W; ++x) {
-                    if (is_rgb) { o[3 * x] = r0[x]; o[3 * x + 1] = r1[x]; o[3 * x + 2] = r2[x]; continue; }
-                    // BT.601 full range, 16-bit fixed point with rounding (ITU-T T.871)
-                    const int Y = r0[x] << 16, cb = r1[x] - 128, cr = r2[x] - 128;
-                    o[3 * x] = clamp8((Y + 91881 * cr + 32768) >> 16);
-                    o[3 * x + 1] = clamp8((Y - 22554 * cb - 46802 * cr + 32768) >> 16);
-                    o[3 * x + 2] = clamp8((Y + 116130 * cb + 32768) >> 16);
-                }
-            }
-            return tex;
+            return assemble();
         }
         p += len;
     }
+    if (progressive && have_frame && scans > 0) return finish_progressive();
     return nullptr;
 }
 

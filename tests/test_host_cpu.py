@@ -234,7 +234,7 @@ def _load_image(host, path):
 
 
 def test_jpeg_textures_decode_like_a_conforming_decoder(host, tmp_path):
-    """image::open() loads JPEG textures too (render.rs:165-181). The host decodes baseline JPEG itself (rr_jpeg.cpp); T.81
+    """image::open() loads JPEG textures too (render.rs:165-181). The host decodes baseline and progressive JPEG itself (rr_jpeg.cpp); T.81
     leaves IDCT and chroma upsampling to the decoder within a level or so, hence the comparison with libjpeg-turbo (PIL) is
     a tolerance, not equality: every texel within 3 levels, 99 % within 1 (4:4:4, no upsampling: within 2)."""
     from PIL import Image
@@ -264,9 +264,19 @@ def test_jpeg_textures_decode_like_a_conforming_decoder(host, tmp_path):
     grey = tmp_path / "grey.jpg"
     Image.fromarray(img[:, :, 0]).save(grey, "JPEG")
     assert _load_image(host, grey) == -2           # ImageLuma8: ignored by render.rs:251
-    prog = tmp_path / "prog.jpg"
-    Image.fromarray(img).save(prog, "JPEG", progressive=True)
-    assert _load_image(host, prog) == -2           # progressive frames: outside this decoder (deviation 4)
+    # progressive frames (spectral selection + successive approximation; libjpeg's default scan script), also with restart
+    # intervals and subsampled chroma
+    for name, kw in (("p444", dict(subsampling=0)), ("p420", dict(subsampling=2, quality=80)),
+                     ("p422rst", dict(subsampling=1, restart_marker_blocks=3)), ("p420small", dict(subsampling=2))):
+        path = tmp_path / f"{name}.jpg"
+        src = small if name == "p420small" else img
+        Image.fromarray(src).save(path, "JPEG", progressive=True, quality=kw.pop("quality", 90), **kw)
+        assert b"\xff\xc2" in path.read_bytes()    # SOF2
+        ref = np.asarray(Image.open(path).convert("RGB")).astype(int)
+        got = _load_image(host, path)
+        assert isinstance(got, np.ndarray) and got.shape == ref.shape, (name, got)
+        d = np.abs(got.astype(int) - ref)
+        assert d.max() <= 3 and (d <= 1).mean() >= 0.99, (name, int(d.max()), float((d <= 1).mean()))
     trunc = tmp_path / "trunc.jpg"
     trunc.write_bytes((tmp_path / "t_420.jpg").read_bytes()[:300])
     assert _load_image(host, trunc) == -2

@@ -1,6 +1,7 @@
 // Mutation fuzzer of the baseline JPEG texture decoder (host/rr_jpeg.cpp). Build with -fsanitize=address,undefined:
 //   g++ -O1 -g -std=c++17 -fsanitize=address,undefined -fno-sanitize-recover=all -Iray-rust_b200/host -Iinclude tools/fuzz/fuzz_jpeg.cpp ray-rust_b200/host/rr_jpeg.cpp ray-rust_b200/host/rr_png.cpp -lz -pthread -o /tmp/fuzz_jpeg && /tmp/fuzz_jpeg seed1.jpg seed2.jpg ...
-// (30 000 mutated files from three PIL-written seeds: no sanitizer report; that run found the 32-bit IDCT overflow the decoder now avoids)
+// FUZZ_SEED / FUZZ_N choose the RNG seed and the number of mutated files (default 30 000). Runs over baseline and progressive
+// PIL-written seeds found (and the decoder now avoids) a 32-bit IDCT overflow and a row overrun with non-integer sampling ratios.
 #include "rr_host.hpp"
 #include <cstdio>
 #include <cstdlib>
@@ -13,9 +14,10 @@ int main(int argc, char **argv) {
         while ((n = fread(b, 1, sizeof b, f)) > 0) d.insert(d.end(), b, b + n);
         fclose(f); seeds.push_back(d);
     }
-    std::mt19937 rng(12345);
+    std::mt19937 rng(getenv("FUZZ_SEED") ? (unsigned)atol(getenv("FUZZ_SEED")) : 12345u);
+    const int iters = getenv("FUZZ_N") ? atoi(getenv("FUZZ_N")) : 30000;
     long ok = 0, total = 0;
-    for (int it = 0; it < 30000; ++it) {
+    for (int it = 0; it < iters; ++it) {
         std::vector<uint8_t> d = seeds[rng() % seeds.size()];
         int kind = rng() % 4;
         if (kind == 0) d.resize(rng() % (d.size() + 1));
